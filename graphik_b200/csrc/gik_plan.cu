@@ -1,0 +1,226 @@
+// gik_plan.cu -- plan creation / destruction, error reporting.
+//
+// A plan is the goal-independent, device-resident description of one robot +
+// environment: what the reference rebuilds per goal through networkx
+// (graph_base.py:171-180, dgp.py:42-65,124-147, graph_base.py:262-279) compiled
+// once into node-centric slot tables for the group kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "gik_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gik_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gik_check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return GIK_OK;
+    gik_set_error("CUDA error %s (%s) in %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+    return GIK_ECUDA;
+}
+
+extern "C" const char *gik_last_error(void) { return g_err; }
+extern "C" int gik_version(void) { return 100; }
+
+extern "C" int gik_default_opts(GikSolveOpts *o)
+{
+    if (!o) { gik_set_error("gik_default_opts: null"); return GIK_EINVAL; }
+    o->mingradnorm = 0.5 * 1e-9;     // riemannian_solver.py:45
+    o->maxiter = 3000;               // :47
+    o->theta = 1.0;                  // :48
+    o->kappa = 0.1;                  // :49
+    o->rho_prime = 0.1;              // trust_region.py:90
+    o->rho_regularization = 1e3;     // :92
+    o->mininner = 1;                 // :116
+    o->maxinner = 10000;             // :118
+    o->Delta_bar = 13.0;             // fixed_rank_psd_sym.py:72 (10 + k)
+    o->Delta0 = 13.0 / 8;            // trust_region.py:137-138
+    return GIK_OK;
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t count)
+{
+    *dst = nullptr;
+    if (count == 0) return GIK_OK;
+    GIK_CUDA(cudaMalloc((void **)dst, count * sizeof(T)));
+    GIK_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return GIK_OK;
+}
+
+static void inv4(const double *T, double *out)
+{
+    // rigid transform inverse
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[r * 4 + c] = T[c * 4 + r];
+    for (int r = 0; r < 3; ++r)
+        out[r * 4 + 3] = -(out[r * 4 + 0] * T[3] + out[r * 4 + 1] * T[7] + out[r * 4 + 2] * T[11]);
+    out[12] = out[13] = out[14] = 0.0;
+    out[15] = 1.0;
+}
+
+static void mul4(const double *A, const double *B, double *C)
+{
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[r * 4 + k] * B[k * 4 + c];
+            C[r * 4 + c] = s;
+        }
+}
+
+extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
+{
+    if (!d || !out) { gik_set_error("gik_plan_create: null argument"); return GIK_EINVAL; }
+    *out = nullptr;
+    const int N = d->n_nodes;
+    if (N < 2 || N > 65535) { gik_set_error("gik_plan_create: n_nodes=%d out of range", N); return GIK_EINVAL; }
+    if (d->n_terms < 0 || (d->n_terms && (!d->term_i || !d->term_j || !d->term_kind || !d->term_target))) {
+        gik_set_error("gik_plan_create: term arrays missing");
+        return GIK_EINVAL;
+    }
+    if (d->n_goal > 4094) { gik_set_error("gik_plan_create: n_goal=%d exceeds 4094", d->n_goal); return GIK_ELIMIT; }
+
+    GikPlan *p = new GikPlan();
+    memset(p, 0, sizeof(*p));
+    int rc = GIK_OK;
+    cudaGetDevice(&p->device);
+    cudaDeviceProp prop;
+    if ((rc = gik_check_cuda(cudaGetDeviceProperties(&prop, p->device), "cudaGetDeviceProperties"))) { delete p; return rc; }
+    p->sm_count = prop.multiProcessorCount;
+    p->N = N;
+    p->n_terms = d->n_terms;
+    p->n_goal = d->n_goal;
+    p->n_anchor = d->n_anchor;
+    p->goal_p = d->goal_p;
+    p->goal_q = d->goal_q;
+    p->axis_length = d->axis_length;
+    p->n_joints = d->n_joints;
+    p->n_goal_edges = d->n_goal_edges;
+
+    // group geometry
+    if (N <= 16) { p->W = 16; p->NPL = 1; }
+    else if (N <= 32) { p->W = 32; p->NPL = 1; }
+    else if (N <= 64) { p->W = 32; p->NPL = 2; }
+    else if (N <= 128) { p->W = 32; p->NPL = 4; }
+    else {
+        gik_set_error("gik_plan_create: n_nodes=%d exceeds the compiled limit of 128", N);
+        delete p;
+        return GIK_ELIMIT;
+    }
+    const int NP = p->W * p->NPL;
+
+    // node-centric slot tables
+    std::vector<int32_t> deg(NP, 0);
+    for (int t = 0; t < d->n_terms; ++t) {
+        const int i = d->term_i[t], j = d->term_j[t];
+        if (i < 0 || j < 0 || i >= N || j >= N || i == j || d->term_kind[t] < 0 || d->term_kind[t] > 2) {
+            gik_set_error("gik_plan_create: bad term %d (i=%d j=%d kind=%d)", t, i, j, d->term_kind[t]);
+            delete p;
+            return GIK_EINVAL;
+        }
+        const int gs = d->term_goal ? d->term_goal[t] : -1;
+        if (gs >= d->n_goal) { gik_set_error("gik_plan_create: term %d goal slot %d >= n_goal", t, gs); delete p; return GIK_EINVAL; }
+        deg[i]++;
+        deg[j]++;
+    }
+    int maxdeg = 1;
+    for (int i = 0; i < N; ++i) maxdeg = deg[i] > maxdeg ? deg[i] : maxdeg;
+    p->maxdeg = maxdeg;
+    std::vector<uint32_t> info((size_t)maxdeg * N, 0u);
+    std::vector<double> target((size_t)maxdeg * N, 0.0);
+    std::vector<int32_t> fill(N, 0);
+    for (int t = 0; t < d->n_terms; ++t) {
+        const int i = d->term_i[t], j = d->term_j[t];
+        const int gs = d->term_goal ? d->term_goal[t] : -1;
+        const uint32_t kg = ((uint32_t)d->term_kind[t] << 16) | ((uint32_t)(gs + 1) << 20);
+        int k = fill[i]++;
+        info[(size_t)k * N + i] = (uint32_t)j | kg;
+        target[(size_t)k * N + i] = d->term_target[t];
+        k = fill[j]++;
+        info[(size_t)k * N + j] = (uint32_t)i | kg;
+        target[(size_t)k * N + j] = d->term_target[t];
+    }
+
+    // omega edge list for the initialisation's linear projection
+    std::vector<int32_t> oi, oj;
+    if (d->omega)
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j)
+                if (d->omega[(size_t)i * N + j]) { oi.push_back(i); oj.push_back(j); }
+    p->n_omega_edges = (int)oi.size();
+
+    // joint-recovery tables (graph_revolute.py:283-310)
+    std::vector<double> Trel, qs0;
+    if (d->n_joints > 0 && d->T0) {
+        const int n = d->n_joints;
+        Trel.resize((size_t)n * 16);
+        qs0.resize((size_t)n * 3);
+        for (int i = 1; i <= n; ++i) {
+            double inv[16], Tq[16], rel[16];
+            inv4(d->T0 + (size_t)(i - 1) * 16, inv);
+            mul4(inv, d->T0 + (size_t)i * 16, &Trel[(size_t)(i - 1) * 16]);
+            memcpy(Tq, d->T0 + (size_t)i * 16, sizeof(Tq));
+            for (int r = 0; r < 3; ++r) Tq[r * 4 + 3] += d->axis_length * Tq[r * 4 + 2];
+            mul4(inv, Tq, rel);
+            for (int r = 0; r < 3; ++r) qs0[(size_t)(i - 1) * 3 + r] = rel[r * 4 + 3];
+        }
+        // final-joint correction applies when the last offset is along z (graph_revolute.py:314)
+        const double *tr = &Trel[(size_t)(n - 1) * 16];
+        const double cx = tr[7] * 1.0 - 0.0, cy = 0.0 - tr[3] * 1.0;  // cross(t, e_z) = (t_y, -t_x, 0)
+        p->last_joint_z_aligned = sqrt(cx * cx + cy * cy) < 1e-10;
+    }
+
+    bool ok = true;
+    ok = ok && !upload(&p->slot_info, info.data(), info.size());
+    ok = ok && !upload(&p->slot_target, target.data(), target.size());
+    ok = ok && !upload(&p->deg, deg.data(), deg.size());
+    ok = ok && !upload(&p->anchor_node, d->anchor_node, (size_t)d->n_anchor);
+    ok = ok && !upload(&p->anchor_pos, d->anchor_pos, (size_t)d->n_anchor * 3);
+    if (d->bs_lower && d->bs_upper) {
+        ok = ok && !upload(&p->bs_lower, d->bs_lower, (size_t)N * N);
+        ok = ok && !upload(&p->bs_upper, d->bs_upper, (size_t)N * N);
+    }
+    ok = ok && !upload(&p->goal_edge_i, d->goal_edge_i, (size_t)d->n_goal_edges);
+    ok = ok && !upload(&p->goal_edge_j, d->goal_edge_j, (size_t)d->n_goal_edges);
+    ok = ok && !upload(&p->goal_edge_slot, d->goal_edge_slot, (size_t)d->n_goal_edges);
+    ok = ok && !upload(&p->omega_i, oi.data(), oi.size());
+    ok = ok && !upload(&p->omega_j, oj.data(), oj.size());
+    if (d->n_joints > 0 && d->T0) {
+        ok = ok && !upload(&p->T0, d->T0, (size_t)(d->n_joints + 1) * 16);
+        ok = ok && !upload(&p->Trel, Trel.data(), Trel.size());
+        ok = ok && !upload(&p->qs0, qs0.data(), qs0.size());
+    }
+    if (!ok) { gik_plan_destroy(p); return GIK_ECUDA; }
+    *out = p;
+    return GIK_OK;
+}
+
+extern "C" int gik_plan_destroy(GikPlan *p)
+{
+    if (!p) return GIK_OK;
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->anchor_node, p->anchor_pos, p->bs_lower,
+                    p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
+                    p->omega_j, p->T0, p->Trel, p->qs0};
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    delete p;
+    return GIK_OK;
+}
+
+extern "C" int gik_plan_info(const GikPlan *p, int32_t what[8])
+{
+    if (!p || !what) { gik_set_error("gik_plan_info: null argument"); return GIK_EINVAL; }
+    what[0] = p->N; what[1] = p->n_terms; what[2] = p->n_goal; what[3] = p->maxdeg;
+    what[4] = p->n_joints; what[5] = p->W; what[6] = p->NPL; what[7] = p->sm_count;
+    return GIK_OK;
+}

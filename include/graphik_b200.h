@@ -1,0 +1,179 @@
+/*
+ * graphik_b200.h -- C ABI of libgraphik_b200.so
+ *
+ * Batched distance-geometric inverse kinematics on NVIDIA B200 (sm_100a).
+ * This is the drop-in boundary for the Riemannian IK hot path of
+ * utiasSTARS/GraphIK.  The reference is pure Python; its only native plug-in
+ * for this path is the numba-AOT extension module `costgrd`
+ * (graphik/solvers/costs.py:3-5,208-209, imported at
+ * graphik/solvers/riemannian_solver.py:18-21).  Each entry point below names
+ * the reference routine it replaces, evaluated for B goal poses per call.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative GIK_E* code on failure;
+ *     gik_last_error() returns a thread-local message.  Nothing throws.
+ *   - All array arguments except GikPlanDesc's are DEVICE pointers owned by the
+ *     caller (e.g. torch tensors); the library allocates only inside
+ *     gik_plan_create.  All floating-point data is IEEE double, row-major.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls
+ *     are asynchronous on that stream.  A plan is immutable after creation and
+ *     may be shared between streams; it belongs to the device that was current
+ *     when it was created.
+ *   - Point sets are Y[B][N][3]; node order is the ProblemGraph's node order
+ *     (p0, x, y, q0, p1, q1, ..., pn, qn, obstacles...).
+ */
+#ifndef GRAPHIK_B200_H
+#define GRAPHIK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIK_OK 0
+#define GIK_EINVAL (-1)   /* bad argument */
+#define GIK_ECUDA (-2)    /* CUDA runtime error (message has the details) */
+#define GIK_ELIMIT (-3)   /* problem exceeds a compiled-in limit */
+
+/* cost-term kinds (riemannian_solver.py:121-138 / costs.py:79-93) */
+#define GIK_TERM_EQ 0     /* omega_ij > 0 : (D_ij - d_ij)^2            */
+#define GIK_TERM_LO 1     /* psi_L,ij > 0 : max(psi_L,ij - d_ij, 0)^2  */
+#define GIK_TERM_UP 2     /* psi_U,ij > 0 : max(d_ij - psi_U,ij, 0)^2  */
+
+/* per-problem status written by gik_rtr_solve */
+#define GIK_STATUS_CONVERGED 0   /* gradnorm < mingradnorm            */
+#define GIK_STATUS_MAXITER 1     /* outer iterations reached maxiter  */
+#define GIK_STATUS_NAN 2         /* non-finite cost at the start      */
+
+typedef struct GikPlan GikPlan;
+
+/*
+ * Host-side description of one robot + environment (goal independent).  It is
+ * what graph.from_pose / distance_matrix_from_graph / adjacency_matrix_from_graph
+ * / distance_bound_matrices (graph_base.py:171-180,262-279; dgp.py:42-65) produce
+ * per goal in the reference, factored into a static part and the few entries
+ * that depend on the goal pose.
+ */
+typedef struct {
+    int32_t n_nodes;            /* N */
+    /* cost terms, one per (i<j, kind); order = the reference's `inds` order */
+    int32_t n_terms;
+    const int32_t *term_i;
+    const int32_t *term_j;
+    const int32_t *term_kind;   /* GIK_TERM_* */
+    const double *term_target;  /* squared distance / squared limit; ignored if term_goal >= 0 */
+    const int32_t *term_goal;   /* >= 0: target is goal_d2[b][term_goal]; -1: static */
+    int32_t n_goal;             /* row length of goal_d2 (= 2 * n_anchor for pose goals) */
+    /* goal assembly (_pose_goal, graph_revolute.py:243-249) */
+    int32_t n_anchor;           /* nodes with a fixed known position */
+    const int32_t *anchor_node; /* [n_anchor] */
+    const double *anchor_pos;   /* [n_anchor][3] */
+    int32_t goal_p, goal_q;     /* node indices of p_n and q_n */
+    double axis_length;
+    /* bound smoothing (dgp.py:192-231): static edge bounds, unsquared;
+     * no edge: lower = 0, upper = +inf.  Goal edges (anchor x {p_n,q_n} without a
+     * static distance) are listed separately and take sqrt(goal_d2) per goal. */
+    const double *bs_lower;     /* [N][N] */
+    const double *bs_upper;     /* [N][N] */
+    int32_t n_goal_edges;
+    const int32_t *goal_edge_i; /* [n_goal_edges] */
+    const int32_t *goal_edge_j;
+    const int32_t *goal_edge_slot; /* index into goal_d2 row */
+    /* initialisation (riemannian_solver.py:67-75): adjacency incl. goal edges */
+    const uint8_t *omega;       /* [N][N] 0/1, may be NULL if gik_init is not used */
+    /* joint recovery (graph_revolute.py:251-318) */
+    int32_t n_joints;           /* 0: tables absent */
+    const double *T0;           /* [(n_joints+1)][4][4] zero-configuration frames */
+} GikPlanDesc;
+
+/* Options of the trust-region solve; defaults = riemannian_solver.py:44-50 over
+ * trust_region.py:85-122 and fixed_rank_psd_sym.py:72. */
+typedef struct {
+    double mingradnorm;         /* 5e-10 */
+    int32_t maxiter;            /* 3000  */
+    double theta;               /* 1.0   */
+    double kappa;               /* 0.1   */
+    double rho_prime;           /* 0.1   */
+    double rho_regularization;  /* 1e3   */
+    int32_t mininner;           /* 1     */
+    int32_t maxinner;           /* 10000 */
+    double Delta_bar;           /* 13 = typicaldist = 10 + k */
+    double Delta0;              /* Delta_bar / 8 */
+} GikSolveOpts;
+
+const char *gik_last_error(void);
+int gik_version(void);
+
+/* Fills *opts with the reference defaults. */
+int gik_default_opts(GikSolveOpts *opts);
+
+int gik_plan_create(const GikPlanDesc *desc, GikPlan **plan_out);
+int gik_plan_destroy(GikPlan *plan);
+/* what[0]=N, [1]=n_terms, [2]=n_goal, [3]=max node degree (slots), [4]=n_joints,
+ * [5]=lanes per problem chosen for gik_rtr_solve, [6]=nodes per lane */
+int gik_plan_info(const GikPlan *plan, int32_t what[8]);
+
+/* _pose_goal + graph_complete_edges for the goal-dependent entries only
+ * (graph_revolute.py:243-249, dgp.py:124-147):
+ * T_goal[B][4][4] -> goal_d2[B][n_goal] squared distances
+ * ([a] = |p_n - anchor_a|^2, [n_anchor + a] = |q_n - anchor_a|^2). */
+int gik_goal_distances(const GikPlan *plan, const double *T_goal, int32_t B, double *goal_d2,
+                       void *stream);
+
+/* costgrd.lcost / lgrad / lcost_and_grad (costs.py:79-169); with a plan holding
+ * only EQ terms: jcost / jgrad / jcost_and_grad (costs.py:7-77).
+ * f[B] and/or g[B][N][3] may be NULL.  g is the reference's HALF gradient. */
+int gik_cost_grad(const GikPlan *plan, const double *Y, const double *goal_d2, int32_t B,
+                  double *f, double *g, void *stream);
+
+/* costgrd.lhess / jhess (costs.py:171-207, 38-58): HW[B][N][3] = ehess(Y)[W]. */
+int gik_hessvec(const GikPlan *plan, const double *Y, const double *W, const double *goal_d2,
+                int32_t B, double *HW, void *stream);
+
+/* PSDFixedRank.proj (fixed_rank_psd_sym.py:91-113), dim = 3:
+ * out[B][N][3] = Z - Y * Omega,  Omega X + X Omega = Y^T Z - Z^T Y. */
+int gik_proj(int32_t N, const double *Y, const double *Z, int32_t B, double *out, void *stream);
+
+/* bound_smoothing (dgp.py:192-231) for B goals: lb, ub [B][N][N] (unsquared). */
+int gik_bounds(const GikPlan *plan, const double *goal_d2, int32_t B, double *lb, double *ub,
+               void *stream);
+
+/* RiemannianSolver.generate_initialization (riemannian_solver.py:67-75; dgp.py:28-31,
+ * 150-183) from bounds: lb, ub [B][N][N] -> Y_init[B][N][3]. */
+int gik_init(const GikPlan *plan, const double *lb, const double *ub, int32_t B, double *Y_init,
+             void *stream);
+
+/* bound_smoothing + generate_initialization fused (bounds never leave the SM):
+ * goal_d2[B][n_goal] -> Y_init[B][N][3]. */
+int gik_bounds_init(const GikPlan *plan, const double *goal_d2, int32_t B, double *Y_init,
+                    void *stream);
+
+/* TrustRegions.solve + _truncated_conjugate_gradient on PSDFixedRank(N, 3)
+ * (trust_region.py:112-599; fixed_rank_psd_sym.py; riemannian_solver.py:178-218)
+ * for B problems in one persistent launch.
+ *   Y_init[B][N][3]        starting points
+ *   Y_out[B][N][3], f[B], gradnorm[B], iters[B], status[B]  = optlog final_values
+ *   n_inner[B]  (may be NULL) Hessian-vector products spent per problem
+ *   trace (may be NULL): [B][trace_rows][6] per outer iteration
+ *       (Delta, numit, stop_reason, fx_prop, accepted, gradnorm)
+ *   work_counter: device int32 scratch, zeroed by the call (persistent work queue). */
+int gik_rtr_solve(const GikPlan *plan, const double *goal_d2, const double *Y_init, int32_t B,
+                  const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
+                  int32_t *iters, int32_t *status, int32_t *n_inner, double *trace,
+                  int32_t trace_rows, int32_t *work_counter, void *stream);
+
+/* ProblemGraphRevolute.joint_variables (graph_revolute.py:251-318):
+ * Y[B][N][3] (+ T_goal[B][4][4] or NULL) -> q[B][n_joints]. */
+int gik_joints(const GikPlan *plan, const double *Y, const double *T_goal, int32_t B, double *q,
+               void *stream);
+
+/* RobotRevolute.pose for every joint + graph.realization points
+ * (robot_revolute.py:85-103, graph_base.py:112-121):
+ * q[B][n_joints] -> T_ee[B][4][4] (may be NULL), Y[B][N][3] (may be NULL). */
+int gik_fk(const GikPlan *plan, const double *q, int32_t B, double *T_ee, double *Y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHIK_B200_H */

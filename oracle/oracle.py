@@ -193,20 +193,34 @@ def gram_from_distance_matrix(D):
     return -0.5 * J @ D @ J
 
 
-def factor(A):
-    """dgp.py:150-159."""
-    n = A.shape[0]
+def canonical_signs(V):
+    """Make the entry of largest magnitude of every column positive (first on ties)."""
+    V = V.copy()
+    for c in range(V.shape[1]):
+        k = int(np.argmax(np.abs(V[:, c])))
+        if V[k, c] < 0:
+            V[:, c] = -V[:, c]
+    return V
+
+
+def factor(A, signs="lapack"):
+    """dgp.py:150-159.  `signs`: eigenvector sign convention -- "lapack" keeps what
+    numpy/LAPACK returns (what the reference inherits), "canonical" applies
+    canonical_signs (what the CUDA kernel does, see gik_bounds_init.cu)."""
     evals, evecs = np.linalg.eigh(A)
+    if signs == "canonical":
+        evecs = canonical_signs(evecs)
     evals[evals < 0] = 0
     X = evecs.dot(np.diag(np.sqrt(evals)))
     return np.fliplr(X)
 
 
-def MDS(B, eps=1e-5):
+def MDS(B, eps=1e-5, signs="lapack"):
     """dgp.py:163-171 -- including the eigh() of the NON-symmetric factor (numpy reads
-    the lower triangle) that sets the kept rank K."""
+    the lower triangle) that sets the kept rank K.  NB: K is not invariant to the signs
+    of the eigenvectors inside `factor`, which LAPACK leaves arbitrary."""
     n = B.shape[0]
-    x = factor(B)
+    x = factor(B, signs)
     evals, _ = np.linalg.eigh(x)
     K = int(np.sum(evals > eps))
     if K < n:
@@ -223,8 +237,8 @@ def linear_projection(P, F, dim):
     return P @ np.fliplr(eigvec)[:, :dim]
 
 
-def generate_initialization(lb, ub, omega, dim=3):
+def generate_initialization(lb, ub, omega, dim=3, signs="lapack"):
     """riemannian_solver.py:67-75."""
     D_rand = (lb + 0.9 * (ub - lb)) ** 2
-    X_rand = MDS(gram_from_distance_matrix(D_rand), eps=1e-8)
+    X_rand = MDS(gram_from_distance_matrix(D_rand), eps=1e-8, signs=signs)
     return linear_projection(X_rand, omega, dim)

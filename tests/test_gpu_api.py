@@ -1,0 +1,104 @@
+"""The reference-facing Python API on the GPU: same names, arguments and return shapes as
+graphik.solvers.riemannian_solver / graphik.solvers.costgrd / graphik.utils.dgp."""
+import numpy as np
+import pytest
+
+from helpers import golden, load_robot, matrices_for_goal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solve_with_riemannian_readme_usage():
+    """README.md:30-46 / experiments/riemannian_example.py, with the loader and solver swapped."""
+    from graphik_b200.solvers.riemannian_solver import solve_with_riemannian
+    from graphik_b200.utils.roboturdf import load_ur10
+    robot, graph = load_ur10()
+    np.random.seed(0)
+    q_goal = robot.random_configuration()
+    T_goal = robot.pose(q_goal, f"p{robot.n}")
+    q_sol, points = solve_with_riemannian(graph, T_goal, use_jit=False)
+    assert sorted(q_sol) == ["p%d" % i for i in range(1, 7)] and points.shape == (16, 3)
+    T_sol = robot.pose(q_sol, "p6").as_matrix()
+    assert np.linalg.norm(T_sol[:3, 3] - T_goal.as_matrix()[:3, 3]) < 1e-2
+    # the misspelt keyword of the reference README is accepted too
+    q2, _ = solve_with_riemannian(graph, T_goal, jit=True)
+    assert q2 == q_sol   # deterministic
+
+
+def test_riemannian_solver_solve_signature_and_log():
+    from graphik_b200.solvers.riemannian_solver import RiemannianSolver
+    from graphik_b200.utils.dgp import (adjacency_matrix_from_graph, bound_smoothing,
+                                         distance_matrix_from_graph)
+    robot, graph = load_robot("ur10")
+    g = golden("ur10_goals")
+    G = graph.from_pose(g["T_goal"][0])
+    D_goal, omega = distance_matrix_from_graph(G), adjacency_matrix_from_graph(G)
+    assert np.array_equal(D_goal, g["D_goal"][0]) and np.array_equal(omega, g["omega"][0])
+    lb, ub = bound_smoothing(G)
+    assert np.max(np.abs(lb - g["lb"][0])) <= 1e-12 and np.max(np.abs(ub - g["ub"][0])) <= 1e-12
+    solver = RiemannianSolver(graph)
+    sol = solver.solve(D_goal, omega, use_limits=True, bounds=(lb, ub), jit=True)
+    assert sorted(sol) == ["f(x)", "gradnorm", "iterations", "time", "x"]
+    assert sol["f(x)"] < 1e-12 and sol["gradnorm"] < 5e-10 and sol["x"].shape == (16, 3)
+    # injected initial point, no limits, output_log=False returns the points only
+    Y = solver.solve(D_goal, omega, use_limits=False, Y_init=g["Y_init"][0], output_log=False)
+    assert isinstance(Y, np.ndarray) and Y.shape == (16, 3)
+    with pytest.raises(Exception):
+        solver.solve(D_goal, omega)                      # neither bounds nor Y_init (:199-200)
+    with pytest.raises(NotImplementedError):
+        RiemannianSolver(graph, {"solver": "ConjugateGradient"})
+    sol3 = RiemannianSolver(graph, {"maxiter": 5}).solve(D_goal, omega, use_limits=True, Y_init=g["Y_init"][0])
+    assert sol3["iterations"] == 5
+
+
+def test_costgrd_facade_matches_reference_vectors():
+    from graphik_b200.solvers import costgrd
+    from oracle import oracle as orc
+    cv = golden("costgrd_vectors")
+    name = "kuka"
+    D, om, pL, pU = (cv[name + "_" + k] for k in ("D_goal", "omega", "psi_L", "psi_U"))
+    inds, jinds = orc.limit_inds(om, pL, pU), orc.equality_inds(om)
+    Y, W = cv[name + "_Y"][5], cv[name + "_W"][5]
+
+    def close(a, b):
+        return np.max(np.abs(np.asarray(a) - b)) <= 1e-12 * max(1.0, np.max(np.abs(b)))
+
+    assert close(costgrd.lcost(Y, D, om, pL, pU, inds), cv[name + "_lcost"][5])
+    assert close(costgrd.lgrad(Y, D, om, pL, pU, inds), cv[name + "_lgrad"][5])
+    assert close(costgrd.lhess(Y, W, D, om, pL, pU, inds), cv[name + "_lhess"][5])
+    f, g = costgrd.lcost_and_grad(Y, D, om, pL, pU, inds)
+    assert close(f, cv[name + "_lcost"][5]) and close(g, cv[name + "_lgrad"][5])
+    assert close(costgrd.jcost(Y, D, jinds), cv[name + "_jcost"][5])
+    assert close(costgrd.jgrad(Y, D, jinds), cv[name + "_jgrad"][5])
+    assert close(costgrd.jhess(Y, W, D, jinds), cv[name + "_jhess"][5])
+    f, g = costgrd.jcost_and_grad(Y, D, jinds)
+    assert close(f, cv[name + "_jcost"][5]) and close(g, cv[name + "_jgrad"][5])
+
+
+def test_solve_batch_outputs_and_obstacle_anchors():
+    """Batched entry point; KUKA with a few spherical obstacles (reference semantics: anchors only)."""
+    from graphik_b200.solvers.riemannian_solver import solve_batch_with_riemannian
+    from helpers import random_goals
+    robot, graph = load_robot("kuka")
+    for k, c in enumerate(([0.6, 0.1, 0.4], [-0.3, 0.5, 0.8], [0.2, -0.6, 0.3])):
+        graph.add_spherical_obstacle("o%d" % k, np.array(c), 0.1)
+    Q, T = random_goals(robot, 32, seed=9)
+    out = solve_batch_with_riemannian(graph, T)
+    assert out["q"].shape == (32, 7) and out["x"].shape == (32, 21, 3)
+    assert np.mean(out["pos_err"] < 1e-2) >= 0.8
+    assert np.median(out["f(x)"]) < 1e-12
+
+
+def test_multi_gpu_sharding_is_exact():
+    """Sharding the batch over two devices reproduces the single-device results bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from graphik_b200.engine import BatchIK
+    from helpers import random_goals
+    robot, graph = load_robot("ur10")
+    Q, T = random_goals(robot, 64, seed=4)
+    full = BatchIK(graph, device=0).solve(T, check=False)
+    with torch.cuda.device(1):
+        part = BatchIK(graph, device=1).solve(T[32:], check=False)
+    assert np.array_equal(full["x"][32:].cpu().numpy(), part["x"].cpu().numpy())

@@ -1,0 +1,101 @@
+"""Pin the CPU oracle (oracle/) against outputs of the reference itself.
+
+The golden files were produced by oracle/gen_golden.py, which imports the unmodified
+reference from /root/reference (through stand-ins for its un-vendored dependencies) and
+records what its own functions return.  The reference's test-suite holds no fixture for this
+path, so these goldens ARE the pin (DESIGN.md "Oracle").
+"""
+import numpy as np
+import pytest
+
+from helpers import ROBOTS, golden
+from oracle import oracle as orc
+
+
+@pytest.mark.parametrize("name", ["ur10", "kuka", "chain20"])
+def test_costs_bit_exact_vs_reference_costgrd(name):
+    """costs.py via the reference's own numba-AOT build: identical bits."""
+    cv = golden("costgrd_vectors")
+    D, om, pL, pU = (cv[name + "_" + k] for k in ("D_goal", "omega", "psi_L", "psi_U"))
+    PL, PJ = orc.Problem(D, om, pL, pU), orc.Problem(D, om, use_limits=False)
+    for k in range(len(cv[name + "_Y"])):
+        Y, W = cv[name + "_Y"][k], cv[name + "_W"][k]
+        assert PL.cost(Y) == cv[name + "_lcost"][k]
+        assert np.array_equal(PL.grad(Y), cv[name + "_lgrad"][k])
+        assert np.array_equal(PL.hess(Y, W), cv[name + "_lhess"][k])
+        assert PJ.cost(Y) == cv[name + "_jcost"][k]
+        assert np.array_equal(PJ.grad(Y), cv[name + "_jgrad"][k])
+        assert np.array_equal(PJ.hess(Y, W), cv[name + "_jhess"][k])
+        # PSDFixedRank.proj (9x9 LU in LAPACK vs Gaussian elimination here)
+        assert np.max(np.abs(orc.proj(Y, W) - cv[name + "_proj"][k])) <= 1e-13 * np.max(np.abs(W))
+
+
+def test_half_gradient_convention():
+    """every reference gradient is exactly half of d(cost); the Hessian product is
+    the derivative of that half gradient.  Finite differences on the oracle."""
+    g = golden("ur10_goals")
+    P = orc.Problem(g["D_goal"][0], g["omega"][0], g["psi_L"][0], g["psi_U"][0])
+    rng = np.random.default_rng(0)
+    Y, W = g["Y_sol"][0] + 0.1 * rng.normal(size=(16, 3)), rng.normal(size=(16, 3))
+    h = 1e-6
+    fd = (P.cost(Y + h * W) - P.cost(Y - h * W)) / (2 * h)
+    assert abs(fd - 2.0 * np.sum(P.grad(Y) * W)) <= 1e-6 * abs(fd)
+    fd_h = (P.grad(Y + h * W) - P.grad(Y - h * W)) / (2 * h)
+    assert np.max(np.abs(fd_h - P.hess(Y, W))) <= 1e-6 * np.max(np.abs(fd_h))
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_bound_smoothing_vs_reference(name):
+    from helpers import load_robot
+    robot, graph = load_robot(name)
+    g = golden(name + "_goals")
+    for k in range(len(g["f"])):
+        G = graph.from_pose(g["T_goal"][k])
+        lb, ub = orc.bound_smoothing(G.edge, G.lower, G.upper)
+        assert np.max(np.abs(lb - g["lb"][k])) <= 1e-13 * np.max(g["ub"][k])
+        assert np.max(np.abs(ub - g["ub"][k])) <= 1e-13 * np.max(g["ub"][k])
+
+
+def test_bound_smoothing_contains_truth():
+    """reference tests/test_bound_smoothing.py:99-117."""
+    from helpers import load_robot, random_goals
+    robot, graph = load_robot("ur10")
+    Q, T = random_goals(robot, 25, seed=22)
+    for k in range(len(Q)):
+        G = graph.from_pose(T[k])
+        lb, ub = orc.bound_smoothing(G.edge, G.lower, G.upper)
+        D = graph.distance_matrix_from_joints(Q[k])
+        assert np.all(D < ub ** 2 + 1e-6) and np.all(lb ** 2 - 1e-6 < D)
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_initialisation_vs_reference(name):
+    g = golden(name + "_goals")
+    for k in range(len(g["f"])):
+        Y = orc.generate_initialization(g["lb"][k], g["ub"][k], g["omega"][k], signs="lapack")
+        assert np.max(np.abs(Y - g["Y_init"][k])) <= 1e-11 * np.max(np.abs(g["Y_init"][k]))
+
+
+@pytest.mark.parametrize("name", ["ur10", "kuka", "lwa4d", "lwa4p", "chain20"])
+def test_trust_region_vs_reference_trace(name):
+    """TrustRegions.solve + tCG: the per-outer-iteration decisions (tCG iteration count, stop
+    reason, accept/reject) recorded from the reference are reproduced for the leading iterations;
+    RTR is chaotic w.r.t. rounding (inner products are summed in a different order than BLAS),
+    so trajectories part ways after that and the end state is compared by quality."""
+    g = golden(name + "_goals")
+    leads = []
+    for k in range(len(g["f"])):
+        P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
+        s = P.solve(g["Y_init"][k], trace_rows=64)
+        ref = g["trace"][k][:g["iterations"][k]]
+        m = min(len(ref), len(s["trace"]), 64)
+        same = np.all(s["trace"][:m][:, [1, 2, 4]] == ref[:m][:, [1, 2, 4]], axis=1)
+        lead = m if same.all() else int(np.argmin(same))
+        leads.append(lead)
+        assert lead >= min(5, m), (name, k, lead)
+        np.testing.assert_allclose(s["trace"][:5, 3], ref[:5, 3], rtol=1e-9)   # fx_prop
+        np.testing.assert_allclose(s["trace"][:5, 0], ref[:5, 0], rtol=0)      # Delta
+        assert abs(P.cost(g["Y_init"][k]) - g["f0"][k]) <= 1e-12 * g["f0"][k]
+        if g["f"][k] < 1e-12:
+            assert s["f(x)"] < 1e-11 and s["gradnorm"] < 5e-10
+    assert np.median(leads) >= 8, leads
