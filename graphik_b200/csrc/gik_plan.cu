@@ -151,6 +151,35 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         target[(size_t)k * N + j] = d->term_target[t];
     }
 
+    // lane-centric tables for k_rtr_fast: lane l serves node l / LPN and owns the slots
+    // k = l % LPN, l % LPN + LPN, ... of that node; unused entries are inert (kind 3, self)
+    std::vector<uint32_t> finfo;
+    std::vector<double> ftarget;
+    p->fast_LPN = 0;
+    p->fast_SPL = 0;
+    if (N <= 32) {
+        const int LPN = N <= 16 ? 2 : 1;
+        const int SPL = (maxdeg + LPN - 1) / LPN;
+        if (SPL <= GIK_FAST_ROWS) {
+            p->fast_LPN = LPN;
+            p->fast_SPL = SPL;
+            finfo.assign((size_t)GIK_FAST_ROWS * 32, 0u);
+            ftarget.assign((size_t)GIK_FAST_ROWS * 32, 0.0);
+            for (int l = 0; l < 32; ++l) {
+                const int node = l / LPN, sub = l % LPN;
+                for (int s = 0; s < GIK_FAST_ROWS; ++s) {
+                    const int k = sub + s * LPN;
+                    if (node < N && k < deg[node]) {
+                        finfo[(size_t)s * 32 + l] = info[(size_t)k * N + node];
+                        ftarget[(size_t)s * 32 + l] = target[(size_t)k * N + node];
+                    } else {
+                        finfo[(size_t)s * 32 + l] = (uint32_t)(node < N ? node : 0) | (3u << 16);
+                    }
+                }
+            }
+        }
+    }
+
     // omega edge list for the initialisation's linear projection
     std::vector<int32_t> oi, oj;
     if (d->omega)
@@ -184,6 +213,8 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->slot_info, info.data(), info.size());
     ok = ok && !upload(&p->slot_target, target.data(), target.size());
     ok = ok && !upload(&p->deg, deg.data(), deg.size());
+    ok = ok && !upload(&p->fast_info, finfo.data(), finfo.size());
+    ok = ok && !upload(&p->fast_target, ftarget.data(), ftarget.size());
     ok = ok && !upload(&p->anchor_node, d->anchor_node, (size_t)d->n_anchor);
     ok = ok && !upload(&p->anchor_pos, d->anchor_pos, (size_t)d->n_anchor * 3);
     if (d->bs_lower && d->bs_upper) {
@@ -208,7 +239,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->anchor_node, p->anchor_pos, p->bs_lower,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};
     for (void *q : ptrs)

@@ -25,30 +25,14 @@
 //     reductions (7 and 3 scalars) instead of six.
 //   * pymanopt's redundant egrad(x) inside every Hessian call is dropped.
 //   * cost and gradient of the proposal are evaluated in one pass.
+#include <cstdlib>
+
 #include "gik_common.cuh"
+#include "gik_rtr.cuh"
 
 namespace {
 
 constexpr int kThreads = 128;
-
-enum { NEGATIVE_CURVATURE = 0, EXCEEDED_TR, REACHED_TARGET_LINEAR, REACHED_TARGET_SUPERLINEAR,
-       MAX_INNER_ITER, MODEL_INCREASED };
-
-struct RtrArgs {
-    const uint32_t *slot_info;
-    const double *slot_target;
-    const int32_t *deg;
-    int N, n_goal, maxdeg, tables_in_smem;
-    const double *goal_d2;
-    const double *Y_init;
-    int B;
-    GikSolveOpts o;
-    double *Y_out, *f, *gradnorm;
-    int32_t *iters, *status, *n_inner;
-    double *trace;
-    int trace_rows;
-    int32_t *work_counter;
-};
 
 template <int NPL>
 __device__ __forceinline__ double dot3(const double (&a)[NPL][3], const double (&b)[NPL][3])
@@ -417,6 +401,13 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
     a.Y_out = Y_out; a.f = f; a.gradnorm = gradnorm; a.iters = iters; a.status = status; a.n_inner = n_inner;
     a.trace = trace; a.trace_rows = trace ? trace_rows : 0; a.work_counter = work_counter;
     cudaStream_t st = (cudaStream_t)stream;
+    // N <= 32: one warp per problem with the slot cache in registers (gik_rtr_fast.cu);
+    // GIK_RTR_GENERIC=1 forces the generic group kernel (A/B measurements, tests)
+    const char *force = getenv("GIK_RTR_GENERIC");
+    if (!(force && force[0] == '1')) {
+        const int rc = gik_launch_rtr_fast(p, a, st);
+        if (rc <= 0) return rc;
+    }
     if (p->W == 16) return launch_rtr<16, 1>(p, a, st);
     switch (p->NPL) {
         case 1: return launch_rtr<32, 1>(p, a, st);

@@ -1,0 +1,401 @@
+// gik_rtr_fast.cu -- latency-optimised trust-region solve for graphs with N <= 32 nodes.
+//
+// Same algorithm and same arithmetic conventions as k_rtr (gik_rtr.cu; reference
+// trust_region.py:112-599, costs.py:79-207, fixed_rank_psd_sym.py:91-137), laid out for
+// the critical path of ONE problem, because a batch's wall time is set by its slowest
+// problems (outer iteration counts range from ~50 to the 3000 cap):
+//
+//   * one full warp per problem -- two problems sharing a warp diverge almost always
+//     (ncu: 16.5 of 32 threads active per instruction in k_rtr<16,1>) and serialise;
+//   * LPN lanes per node (LPN = 2 for N <= 16): the lanes of a node split its slot list
+//     and combine the partial sums with one xor-shuffle, halving the serial slot loop;
+//   * everything about an edge term that only depends on the current iterate x --
+//     D_ij = x_i - x_j, the activity of the hinge and the residual -- is cached in
+//     REGISTERS once per accepted outer iteration (SPL slots per lane, compile-time),
+//     so an inner tCG iteration loads only the neighbour's direction delta_j:
+//       Z_i = sum_slots <D', w> D' + c w,   w = delta_i - delta_j,  D' = 2 act D,  c = 2 act r
+//     (= costs.py lhess: 2 * sum act [2 <D,w> D + (d - T) w]);
+//   * the cache is rebuilt by the cost/gradient pass of the proposal x + eta, which the
+//     outer iteration needs anyway (trust_region.py:248-251); a rejected step rebuilds
+//     it at x.
+#include "gik_rtr.cuh"
+
+namespace {
+
+constexpr int kThreads = 32;            // one warp = one problem per CTA: a straggler pins only its own warp's
+                                        // registers, so the next batch's kernel can move in beside it
+constexpr int kWarps = kThreads / 32;
+
+template <int LPN, int K>
+__device__ __forceinline__ void node_allreduce(double (&v)[K])
+{
+#pragma unroll
+    for (int off = 16; off >= LPN; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
+    }
+}
+
+// Transposed butterfly all-reduce of KP (4 or 8) scalars over the nodes of a warp.  At each of
+// the first log2(KP) levels a lane keeps half of its values and ships the other half to its
+// partner, so the shuffle count is KP + 2 * (remaining levels) instead of KP * levels; the
+// totals are then fetched from the lanes that own them.  Every lane ends with identical bits.
+// (ncu on the plain butterfly: SHFL issues at ~4 cycles each and was 23 % of all instructions.)
+template <int LPN, int KP>
+__device__ __forceinline__ void node_allreduce_t(double (&v)[KP], int lane)
+{
+    static_assert(KP == 4 || KP == 8, "KP must be 4 or 8");
+    double cur[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) cur[k] = v[k];
+    int cnt = KP;
+#pragma unroll
+    for (int off = 16; off >= LPN; off >>= 1) {
+        if (cnt > 1) {
+            const int half = cnt / 2;
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < KP / 2; ++k) {
+                if (k < half) {
+                    const double keep = up ? cur[half + k] : cur[k];
+                    const double send = up ? cur[k] : cur[half + k];
+                    cur[k] = keep + __shfl_xor_sync(GIK_FULL_MASK, send, off, 32);
+                }
+            }
+            cnt = half;
+        } else {
+            cur[0] += __shfl_xor_sync(GIK_FULL_MASK, cur[0], off, 32);
+        }
+    }
+    // owner of scalar k: lane bits (16, 8[, 4]) spell k, most significant first
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int src = (KP == 8) ? (((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4)
+                                  : (((k >> 1) & 1) * 16 + (k & 1) * 8);
+        v[k] = __shfl_sync(GIK_FULL_MASK, cur[0], src, 32);
+    }
+}
+
+// sum over the LPN lanes of a node (both lanes end with identical bits)
+template <int LPN, int K>
+__device__ __forceinline__ void pair_combine(double (&v)[K])
+{
+#pragma unroll
+    for (int off = LPN / 2; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
+    }
+}
+
+struct SlotCache {
+    double dx, dy, dz;  // 2 * act * (x_i - x_j): zero for an inactive hinge, so (D.w) D = 4 act <d,w> d
+    double c2;          // 2 * act * (d_ij - T_ij)
+};
+
+template <int LPN, int SPL>
+__global__ void __launch_bounds__(kThreads) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
+                                                       const double *__restrict__ fast_target)
+{
+    constexpr int NPW = 32 / LPN;  // node slots per warp
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int node = lane / LPN;
+    const bool valid = node < a.N;
+    const int goal_pad = (a.n_goal + 1) & ~1;
+    double *P = smem + (size_t)warp * (6 * NPW + goal_pad + SPL * 32);
+    double *V = P + 3 * NPW;
+    double *goal = V + 3 * NPW;
+    double *tgt = goal + goal_pad + lane;   // [SPL][32] per-problem targets of this warp's slots
+    const GikSolveOpts &o = a.o;
+    const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
+
+    // static slot description of this lane (identical for every problem)
+    uint32_t info[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) info[s] = fast_info[s * 32 + lane];
+
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(a.work_counter, 1);
+        b = __shfl_sync(GIK_FULL_MASK, b, 0, 32);
+        if (b >= a.B) break;
+
+        double x[3] = {0.0, 0.0, 0.0}, g[3], eta[3], Heta[3], r[3], dl[3], Hd[3];
+        SlotCache sc[SPL];
+        if (valid) {
+            const double *src = a.Y_init + ((size_t)b * a.N + node) * 3;
+            x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
+        }
+        __syncwarp();
+        for (int k = lane; k < a.n_goal; k += 32) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
+        if (lane % LPN == 0) { P[node] = x[0]; P[NPW + node] = x[1]; P[2 * NPW + node] = x[2]; }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            const uint32_t gs = GIK_SLOT_GOAL(info[s]);
+            tgt[s * 32] = gs ? goal[gs - 1] : fast_target[s * 32 + lane];
+        }
+
+        // cost / gradient at point p (published in P) + rebuild of the slot cache.
+        // Returns this lane's cost share; gout = full half-gradient of the node.
+        auto rebuild = [&](const double (&p)[3], double (&gout)[3]) -> double {
+            double fpart = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+#pragma unroll
+            for (int s = 0; s < SPL; ++s) {
+                const int j = GIK_SLOT_NBR(info[s]);
+                const uint32_t kind = GIK_SLOT_KIND(info[s]);
+                const double dx = p[0] - P[j], dy = p[1] - P[NPW + j], dz = p[2] - P[2 * NPW + j];
+                const double d = dx * dx + dy * dy + dz * dz;
+                double rr = d - tgt[s * 32];
+                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
+                                 ((kind == GIK_TERM_UP) & (rr > 0.0));
+                rr = act ? rr : 0.0;
+                fpart = fma(rr, rr, fpart);
+                gx = fma(rr, dx, gx);
+                gy = fma(rr, dy, gy);
+                gz = fma(rr, dz, gz);
+                const double two = act ? 2.0 : 0.0;
+                sc[s].dx = two * dx; sc[s].dy = two * dy; sc[s].dz = two * dz;
+                sc[s].c2 = 2.0 * rr;
+            }
+            double v[3] = {2.0 * gx, 2.0 * gy, 2.0 * gz};
+            pair_combine<LPN, 3>(v);
+            gout[0] = v[0]; gout[1] = v[1]; gout[2] = v[2];
+            return 0.5 * fpart;
+        };
+
+        double fx, gg, Mi[6];
+        {
+            double f1[1] = {rebuild(x, g)};
+            pair_combine<LPN, 1>(f1);
+            double v[8] = {f1[0], g[0] * g[0] + g[1] * g[1] + g[2] * g[2],
+                           x[0] * x[0], x[0] * x[1], x[0] * x[2], x[1] * x[1], x[1] * x[2], x[2] * x[2]};
+            node_allreduce<LPN, 8>(v);
+            fx = v[0];
+            gg = v[1];
+            gik_sylvester_inverse(v + 2, Mi);
+        }
+        double norm_grad = sqrt(gg);
+        double Delta = o.Delta0;
+        int k_outer = 0, inner_total = 0, status = GIK_STATUS_MAXITER;
+        if (!(isfinite(fx) && isfinite(gg))) {
+            status = GIK_STATUS_NAN;
+        } else {
+            for (;;) {
+                // ================= tCG (trust_region.py:436-599), eta0 = 0, precon = identity
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    eta[q] = 0.0; Heta[q] = 0.0; r[q] = g[q]; dl[q] = -g[q];
+                }
+                double e_Pe = 0.0, r_r = gg;
+                const double norm_r0 = sqrt(r_r);
+                double z_r = r_r, d_Pd = r_r, e_Pd = 0.0, model_value = 0.0;
+                const double pw = o.theta == 1.0 ? norm_r0 : pow(norm_r0, o.theta);
+                const double r_target = norm_r0 * fmin(pw, o.kappa);
+                // sqrt is monotone: ||r|| <= target  <=>  <r,r> <= target^2 (saves a sqrt per inner iteration)
+                const double r_target2 = r_target * r_target;
+                const double Delta2 = Delta * Delta;
+                double inv_z_r = gik_rcp(z_r);  // for beta = z_r_new / z_r, formed one iteration ahead
+                int stop = MAX_INNER_ITER;
+                int j = 0;
+                for (j = 0; j < o.maxinner; ++j) {
+                    // ---- Hdelta = proj(x, lhess(x, delta))
+                    if (lane % LPN == 0) { V[node] = dl[0]; V[NPW + node] = dl[1]; V[2 * NPW + node] = dl[2]; }
+                    __syncwarp();
+                    // two independent accumulator chains (c w and <D', w> D') halve the dependent FMA depth
+                    double z[3] = {0.0, 0.0, 0.0}, zb[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int s = 0; s < SPL; ++s) {
+                        const int jn = GIK_SLOT_NBR(info[s]);
+                        const double wx = dl[0] - V[jn], wy = dl[1] - V[NPW + jn], wz = dl[2] - V[2 * NPW + jn];
+                        const double t = fma(sc[s].dx, wx, fma(sc[s].dy, wy, sc[s].dz * wz));
+                        z[0] = fma(sc[s].c2, wx, z[0]);
+                        z[1] = fma(sc[s].c2, wy, z[1]);
+                        z[2] = fma(sc[s].c2, wz, z[2]);
+                        zb[0] = fma(t, sc[s].dx, zb[0]);
+                        zb[1] = fma(t, sc[s].dy, zb[1]);
+                        zb[2] = fma(t, sc[s].dz, zb[2]);
+                    }
+                    z[0] += zb[0]; z[1] += zb[1]; z[2] += zb[2];
+                    pair_combine<LPN, 3>(z);
+                    double v[8];
+                    v[7] = 0.0;
+                    v[0] = dl[0] * z[0] + dl[1] * z[1] + dl[2] * z[2];
+                    v[1] = z[1] * x[2] - z[2] * x[1];      // c = sum Z_i x Y_i
+                    v[2] = z[2] * x[0] - z[0] * x[2];
+                    v[3] = z[0] * x[1] - z[1] * x[0];
+                    v[4] = dl[1] * x[2] - dl[2] * x[1];    // u = sum delta_i x Y_i
+                    v[5] = dl[2] * x[0] - dl[0] * x[2];
+                    v[6] = dl[0] * x[1] - dl[1] * x[0];
+                    node_allreduce_t<LPN, 8>(v, lane);
+                    double om[3];
+                    gik_sym_mul(Mi, v + 1, om);
+                    Hd[0] = z[0] - (x[1] * om[2] - x[2] * om[1]);
+                    Hd[1] = z[1] - (x[2] * om[0] - x[0] * om[2]);
+                    Hd[2] = z[2] - (x[0] * om[1] - x[1] * om[0]);
+                    const double d_Hd = v[0] - (om[0] * v[4] + om[1] * v[5] + om[2] * v[6]);
+                    ++inner_total;
+                    const double alpha = gik_div(z_r, d_Hd, gik_rcp(d_Hd));
+                    const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+                    // !(d_Hd > 0) also catches NaN (the reference would spin to maxinner on it)
+                    if (!(d_Hd > 0.0) || e_Pe_new >= Delta2) {
+                        const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            eta[q] = fma(tau, dl[q], eta[q]);
+                            Heta[q] = fma(tau, Hd[q], Heta[q]);
+                        }
+                        stop = d_Hd <= 0.0 ? NEGATIVE_CURVATURE : EXCEEDED_TR;
+                        break;
+                    }
+                    e_Pe = e_Pe_new;
+                    double ne[3], nh[3], nr[3], sdot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        ne[q] = fma(alpha, dl[q], eta[q]);
+                        nh[q] = fma(alpha, Hd[q], Heta[q]);
+                        nr[q] = fma(alpha, Hd[q], r[q]);
+                        sdot[0] = fma(ne[q], g[q], sdot[0]);
+                        sdot[1] = fma(ne[q], nh[q], sdot[1]);
+                        sdot[2] = fma(nr[q], nr[q], sdot[2]);
+                    }
+                    node_allreduce_t<LPN, 4>(sdot, lane);
+                    const double new_model_value = sdot[0] + 0.5 * sdot[1];
+                    if (new_model_value >= model_value) {
+                        stop = MODEL_INCREASED;
+                        break;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { eta[q] = ne[q]; Heta[q] = nh[q]; r[q] = nr[q]; }
+                    model_value = new_model_value;
+                    r_r = sdot[2];
+                    if (j >= o.mininner && r_r <= r_target2) {
+                        stop = o.kappa < pw ? REACHED_TARGET_LINEAR : REACHED_TARGET_SUPERLINEAR;
+                        break;
+                    }
+                    const double beta = gik_div(r_r, z_r, inv_z_r);
+                    z_r = r_r;
+                    inv_z_r = gik_rcp(z_r);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) dl[q] = fma(beta, dl[q], -r[q]);
+                    e_Pd = beta * (e_Pd + alpha * d_Pd);
+                    d_Pd = z_r + beta * beta * d_Pd;
+                }
+                const int numit = j < o.maxinner ? j : o.maxinner - 1;
+
+                // ================= proposal x + eta; dl <- x_prop, Hd <- grad(x_prop), cache <- x_prop
+#pragma unroll
+                for (int q = 0; q < 3; ++q) dl[q] = x[q] + eta[q];
+                if (lane % LPN == 0) { P[node] = dl[0]; P[NPW + node] = dl[1]; P[2 * NPW + node] = dl[2]; }
+                __syncwarp();
+                double f1[1] = {rebuild(dl, Hd)};
+                pair_combine<LPN, 1>(f1);
+                double v[10] = {f1[0],
+                                g[0] * eta[0] + g[1] * eta[1] + g[2] * eta[2],
+                                eta[0] * Heta[0] + eta[1] * Heta[1] + eta[2] * Heta[2],
+                                Hd[0] * Hd[0] + Hd[1] * Hd[1] + Hd[2] * Hd[2],
+                                dl[0] * dl[0], dl[0] * dl[1], dl[0] * dl[2], dl[1] * dl[1], dl[1] * dl[2],
+                                dl[2] * dl[2]};
+                node_allreduce<LPN, 10>(v);
+                const double fx_prop = v[0];
+                double rhonum = fx - fx_prop;
+                double rhoden = -v[1] - 0.5 * v[2];
+                const double rho_reg = fmax(1.0, fabs(fx)) * eps * o.rho_regularization;
+                rhonum += rho_reg;
+                rhoden += rho_reg;
+                const bool model_decreased = rhoden >= 0.0;
+                const double rho = rhonum / rhoden;
+                const double Delta_used = Delta;
+                if (rho < 0.25 || !model_decreased || isnan(rho)) {
+                    Delta = Delta / 4.0;
+                } else if (rho > 0.75 && (stop == NEGATIVE_CURVATURE || stop == EXCEEDED_TR)) {
+                    Delta = fmin(2.0 * Delta, o.Delta_bar);
+                }
+                const bool accept = model_decreased && rho > o.rho_prime;
+                if (accept) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { x[q] = dl[q]; g[q] = Hd[q]; }
+                    fx = fx_prop;
+                    gg = v[3];
+                    norm_grad = sqrt(gg);
+                    gik_sylvester_inverse(v + 4, Mi);
+                } else {
+                    // rejected: bring the exchange buffer and the slot cache back to x
+                    __syncwarp();
+                    if (lane % LPN == 0) { P[node] = x[0]; P[NPW + node] = x[1]; P[2 * NPW + node] = x[2]; }
+                    __syncwarp();
+                    double gtmp[3];
+                    rebuild(x, gtmp);
+                }
+                if (a.trace && k_outer < a.trace_rows && lane == 0) {
+                    double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
+                    row[0] = Delta_used;
+                    row[1] = (double)numit;
+                    row[2] = (double)stop;
+                    row[3] = fx_prop;
+                    row[4] = accept ? 1.0 : 0.0;
+                    row[5] = accept ? norm_grad : nan("");
+                }
+                ++k_outer;
+                if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
+                if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
+            }
+        }
+        if (valid && lane % LPN == 0) {
+            double *dst = a.Y_out + ((size_t)b * a.N + node) * 3;
+            dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
+        }
+        if (lane == 0) {
+            a.f[b] = fx;
+            a.gradnorm[b] = norm_grad;
+            a.iters[b] = k_outer;
+            a.status[b] = status;
+            if (a.n_inner) a.n_inner[b] = inner_total;
+        }
+        __syncwarp();
+    }
+}
+
+template <int LPN, int SPL>
+int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+{
+    constexpr int NPW = 32 / LPN;
+    const int goal_pad = (p->n_goal + 1) & ~1;
+    const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32) * sizeof(double);
+    if (smem > 48 * 1024)
+        GIK_CUDA(cudaFuncSetAttribute(k_rtr_fast<LPN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtr_fast<LPN, SPL>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = p->sm_count * per_sm;
+    const int need = (a.B + kWarps - 1) / kWarps;
+    if (blocks > need) blocks = need;
+    GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
+    k_rtr_fast<LPN, SPL><<<blocks, kThreads, smem, st>>>(a, p->fast_info, p->fast_target);
+    return gik_check_cuda(cudaGetLastError(), "k_rtr_fast launch");
+}
+
+}  // namespace
+
+int gik_launch_rtr_fast(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+{
+    if (!p->fast_info) return 1;
+    if (p->fast_LPN == 2) {
+        switch (p->fast_SPL) {
+            case 1: case 2: case 3: case 4: return launch<2, 4>(p, a, st);
+            case 5: return launch<2, 5>(p, a, st);
+            case 6: return launch<2, 6>(p, a, st);
+            case 7: case 8: return launch<2, 8>(p, a, st);
+            default: return 1;
+        }
+    }
+    switch (p->fast_SPL) {
+        case 1: case 2: case 3: case 4: case 5: case 6: return launch<1, 6>(p, a, st);
+        case 7: case 8: return launch<1, 8>(p, a, st);
+        case 9: return launch<1, 9>(p, a, st);
+        case 10: return launch<1, 10>(p, a, st);
+        case 11: case 12: return launch<1, 12>(p, a, st);
+        default: return 1;
+    }
+}
