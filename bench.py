@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="ur10")
     ap.add_argument("--batch", type=int, default=4096, help="goal poses per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="goals per step of the CPU arm / cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="goals per step of the CPU arm / cpu_baseline")
     ap.add_argument("--concurrent", type=int, default=4,
                     help="batches in flight (CUDA streams); 1 = strictly one batch at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")

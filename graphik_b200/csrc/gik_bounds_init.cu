@@ -179,13 +179,15 @@ __global__ void k_bounds_init(const BiArgs a)
     int *order = reinterpret_cast<int *>(rowM + N);  // N ints
     double *mats = rowM + N + (N + 1) / 2 + 1;
     double *M1, *M2, *M3;
-    if (a.use_scratch) {
+    if (a.use_scratch == 2) {          // nothing fits: all three matrices in global scratch
         M1 = a.scratch + (size_t)blockIdx.x * 3 * NN;
+        M2 = M1 + NN;
+        M3 = M2 + NN;
     } else {
         M1 = mats;
+        M2 = M1 + NN;
+        M3 = a.use_scratch == 1 ? a.scratch + (size_t)blockIdx.x * NN : M2 + NN;
     }
-    M2 = M1 + NN;
-    M3 = M2 + NN;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
@@ -369,23 +371,24 @@ int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
     a.goal_edge_slot = p->goal_edge_slot;
     a.omega_i = p->omega_i;
     a.omega_j = p->omega_j;
-    const size_t mat_bytes = (size_t)3 * N * N * sizeof(double);
-    size_t smem = small_bytes(N);
+    const size_t mat = (size_t)N * N * sizeof(double);
+    size_t smem = small_bytes(N) + (p->bi_mode == 0 ? 3 : (p->bi_mode == 1 ? 2 : 0)) * mat;
     int threads = N <= 20 ? 32 : (N <= 48 ? 128 : 256);
     int blocks = a.B;
-    a.use_scratch = 0;
-    a.scratch = nullptr;
-    if (smem + mat_bytes <= 200 * 1024) {
-        smem += mat_bytes;
-    } else {
-        gik_set_error("gik_bounds/gik_init: N=%d needs %zu bytes of shared memory (limit 200 KiB)", N, smem + mat_bytes);
-        return GIK_ELIMIT;
+    a.use_scratch = p->bi_mode;
+    a.scratch = p->bi_scratch;
+    if (p->bi_mode && !p->bi_scratch) {
+        gik_set_error("gik_bounds/gik_init: plan for N=%d was created without bound tables (no scratch)", N);
+        return GIK_EINVAL;
     }
     GIK_CUDA(cudaFuncSetAttribute(k_bounds_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounds_init, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int cap = p->sm_count * per_sm;
+    int cap = p->bi_blocks;
+    if (p->bi_mode == 0) {
+        int per_sm = 0;
+        GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounds_init, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        cap = p->sm_count * per_sm;
+    }
     if (blocks > cap) blocks = cap;
     k_bounds_init<<<blocks, threads, smem, st>>>(a);
     return gik_check_cuda(cudaGetLastError(), "k_bounds_init launch");

@@ -209,6 +209,24 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         p->last_joint_z_aligned = sqrt(cx * cx + cy * cy) < 1e-10;
     }
 
+    // k_bounds_init works on three N x N fp64 matrices per goal: keep them in shared memory when
+    // they fit (227 KB per CTA), else spill the third / all three to an L2-resident scratch
+    {
+        const size_t small = (size_t)((N + 2) + 34 + N + N + (N + 1) / 2 + 1) * sizeof(double);
+        const size_t mat = (size_t)N * N * sizeof(double);
+        const size_t cap = 227 * 1024;
+        p->bi_mode = small + 3 * mat <= cap ? 0 : (small + 2 * mat <= cap ? 1 : 2);
+        p->bi_blocks = p->bi_mode == 1 ? p->sm_count : 2 * p->sm_count;
+        p->bi_scratch = nullptr;
+        if (p->bi_mode) {
+            const size_t count = (size_t)p->bi_blocks * (p->bi_mode == 1 ? 1 : 3) * N * N;
+            if (gik_check_cuda(cudaMalloc((void **)&p->bi_scratch, count * sizeof(double)), "cudaMalloc(bi_scratch)")) {
+                delete p;
+                return GIK_ECUDA;
+            }
+        }
+    }
+
     bool ok = true;
     ok = ok && !upload(&p->slot_info, info.data(), info.size());
     ok = ok && !upload(&p->slot_target, target.data(), target.size());
@@ -239,7 +257,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->anchor_node, p->anchor_pos, p->bs_lower,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};
     for (void *q : ptrs)

@@ -18,6 +18,8 @@
 //   * the cache is rebuilt by the cost/gradient pass of the proposal x + eta, which the
 //     outer iteration needs anyway (trust_region.py:248-251); a rejected step rebuilds
 //     it at x.
+#include <cstdlib>
+
 #include "gik_rtr.cuh"
 
 namespace {
@@ -93,8 +95,8 @@ struct SlotCache {
 };
 
 template <int LPN, int SPL>
-__global__ void __launch_bounds__(kThreads) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
-                                                       const double *__restrict__ fast_target)
+__device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *__restrict__ fast_info,
+                                              const double *__restrict__ fast_target)
 {
     constexpr int NPW = 32 / LPN;  // node slots per warp
     extern __shared__ double smem[];
@@ -357,22 +359,42 @@ __global__ void __launch_bounds__(kThreads) k_rtr_fast(const RtrArgs a, const ui
     }
 }
 
+// Two register budgets of the same body: the default lets ptxas keep the whole slot cache in
+// registers (best single-problem latency); the OCC variant caps registers at 128 for 16 warps per SM
+// (a few spills, more problems resident) -- chosen for large batches, see launch().
+template <int LPN, int SPL>
+__global__ void __launch_bounds__(kThreads) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
+                                                       const double *__restrict__ fast_target)
+{
+    rtr_fast_body<LPN, SPL>(a, fast_info, fast_target);
+}
+
+template <int LPN, int SPL>
+__global__ void __launch_bounds__(kThreads, 16) k_rtr_fast_occ(const RtrArgs a, const uint32_t *__restrict__ fast_info,
+                                                               const double *__restrict__ fast_target)
+{
+    rtr_fast_body<LPN, SPL>(a, fast_info, fast_target);
+}
+
 template <int LPN, int SPL>
 int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
+    const char *occ_env = getenv("GIK_RTR_OCC");
+    const bool occ = occ_env && occ_env[0] == '1';
+    auto kern = occ ? k_rtr_fast_occ<LPN, SPL> : k_rtr_fast<LPN, SPL>;
     constexpr int NPW = 32 / LPN;
     const int goal_pad = (p->n_goal + 1) & ~1;
     const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32) * sizeof(double);
     if (smem > 48 * 1024)
-        GIK_CUDA(cudaFuncSetAttribute(k_rtr_fast<LPN, SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtr_fast<LPN, SPL>, kThreads, smem));
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     int blocks = p->sm_count * per_sm;
     const int need = (a.B + kWarps - 1) / kWarps;
     if (blocks > need) blocks = need;
     GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
-    k_rtr_fast<LPN, SPL><<<blocks, kThreads, smem, st>>>(a, p->fast_info, p->fast_target);
+    kern<<<blocks, kThreads, smem, st>>>(a, p->fast_info, p->fast_target);
     return gik_check_cuda(cudaGetLastError(), "k_rtr_fast launch");
 }
 

@@ -274,6 +274,16 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     problems = {}
     for name in args.robots:
+        if name == "kuka_table":
+            # BASELINE config 3 as the reference literally runs it: KUKA + table_environment()
+            # (utils.py:179-191, experiments/riemannian_example.py:13-17); few goals -- ~20 s each
+            from graphik.utils.utils import table_environment
+            robot, graph = _loaders()["kuka"]()
+            for idx, obs in enumerate(table_environment()):
+                graph.add_spherical_obstacle(f"o{idx}", obs[0], obs[1])
+            np.savez_compressed(os.path.join(GOLDEN, name + "_graph.npz"), **graph_static(graph))
+            problems[name] = dump_goals(name, robot, graph, min(args.goals, 2), args.seed)
+            continue
         if name.startswith("chain"):
             robot, graph, dh = random_dh_chain(int(name[5:]), args.seed)
             dump_model(name, robot, dh)
@@ -282,7 +292,8 @@ def main():
             dump_model(name, robot)
         np.savez_compressed(os.path.join(GOLDEN, name + "_graph.npz"), **graph_static(graph))
         problems[name] = dump_goals(name, robot, graph, args.goals, args.seed)
-    dump_costgrd_vectors({k: v for k, v in problems.items() if k in ("ur10", "kuka", "chain20")})
+    if all(k in problems for k in ("ur10", "kuka", "chain20")):
+        dump_costgrd_vectors({k: v for k, v in problems.items() if k in ("ur10", "kuka", "chain20")})
 
 
 if __name__ == "__main__":

@@ -47,3 +47,13 @@ def align_columns(Y, Yref):
     s = np.sign(np.sum(Y * Yref, axis=-2, keepdims=True))
     s[s == 0] = 1
     return Y * s
+
+
+def load_kuka_table(**kw):
+    """BASELINE config 3 as the reference runs it: KUKA IIWA + table_environment() obstacles
+    (reference semantics: obstacles are anchors only)."""
+    from graphik_b200.utils.utils import table_environment
+    robot, graph = load_robot("kuka", **kw)
+    for k, (c, r) in enumerate(table_environment()):
+        graph.add_spherical_obstacle("o%d" % k, c, r)
+    return robot, graph

@@ -1,0 +1,60 @@
+"""BASELINE config 3 (KUKA IIWA + table_environment(), N = 118 nodes, 5609 equality terms) as a
+parity case: the generic group kernel (4 nodes per lane), bound smoothing and initialisation with
+matrices that no longer fit in shared memory three at a time."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, align_columns, golden, load_kuka_table
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "kuka_table_goals.npz")),
+                                 reason="kuka_table golden not generated")]
+
+
+def test_kuka_table_pipeline_vs_reference():
+    from graphik_b200.engine import BatchIK
+    from oracle import oracle as orc
+    robot, graph = load_kuka_table()
+    g = golden("kuka_table_goals")
+    K = len(g["f"])
+    eng = BatchIK(graph)
+    assert eng.plan.N == 118 and eng.plan.n_terms == 5609 + 9 + 6
+    gd = eng.goal_distances(g["T_goal"])
+    rows = np.stack([eng.plan.goal_row_from_matrix(g["D_goal"][k]) for k in range(K)])
+    assert np.max(np.abs(gd.cpu().numpy() - rows)) <= 1e-15 * np.max(rows)
+    # bound smoothing against the reference's networkx Bellman-Ford
+    lb, ub = eng.bounds(gd)
+    assert np.max(np.abs(ub.cpu().numpy() - g["ub"])) <= 1e-12 * np.max(g["ub"])
+    assert np.max(np.abs(lb.cpu().numpy() - g["lb"])) <= 1e-12 * np.max(g["ub"])
+    # initialisation against the oracle (canonical eigenvector signs)
+    Y0 = eng.initialization(gd).cpu().numpy()
+    for k in range(K):
+        ref = orc.generate_initialization(g["lb"][k], g["ub"][k], g["omega"][k], signs="canonical")
+        err = np.max(np.abs(align_columns(Y0[k], ref) - ref))
+        assert err <= 1e-7 * np.max(np.abs(ref)), (k, err)
+    # cost / gradient / Hessian-vector against the oracle on the reference's matrices
+    rng = np.random.default_rng(0)
+    W = rng.normal(size=g["Y_init"].shape)
+    f, gr = eng.cost_grad(g["Y_init"], rows)
+    hv = eng.hessvec(g["Y_init"], W, rows).cpu().numpy()
+    for k in range(K):
+        P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
+        fo, go, ho = P.cost(g["Y_init"][k]), P.grad(g["Y_init"][k]), P.hess(g["Y_init"][k], W[k])
+        assert abs(float(f[k]) - fo) <= 1e-12 * fo
+        assert np.max(np.abs(gr[k].cpu().numpy() - go)) <= 1e-12 * np.max(np.abs(go))
+        assert np.max(np.abs(hv[k] - ho)) <= 1e-12 * np.max(np.abs(ho))
+    # trust-region solve from the reference's own starting point (bounded: the reference needs up to
+    # 2600 outer iterations here) -- leading decisions against the oracle, then quality
+    from graphik_b200.engine import make_opts
+    out = eng.solve_points(rows, g["Y_init"], trace_rows=16, opts=make_opts({"maxiter": 400}))
+    tr = out["trace"].cpu().numpy()
+    for k in range(K):
+        P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
+        ref = P.solve(g["Y_init"][k], params={"maxiter": 16}, trace_rows=16)["trace"]
+        m = min(len(ref), 4)
+        assert np.array_equal(tr[k, :m][:, [1, 2, 4]], ref[:m][:, [1, 2, 4]]), (k, tr[k, :m], ref[:m])
+        np.testing.assert_allclose(tr[k, :m, 3], ref[:m, 3], rtol=1e-6)
+    f_end = out["f(x)"].cpu().numpy()
+    assert np.all(f_end < 1e-3 * g["f0"]), (f_end, g["f0"])
