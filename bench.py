@@ -186,14 +186,16 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="ur10")
     ap.add_argument("--batch", type=int, default=4096, help="goal poses per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="goals per step of the CPU arm / cpu_baseline")
-    ap.add_argument("--concurrent", type=int, default=4,
+    ap.add_argument("--concurrent", type=int, default=8,
                     help="batches in flight (CUDA streams); 1 = strictly one batch at a time")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "latency", "throughput", "generic"],
+                    help="gik_rtr_solve implementation (same results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -215,13 +217,13 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     robot, graph = load_model(args.robot)
-    # batches in flight; capped by the warm-up count so that every stream/slot is warmed exactly once or more
-    C = max(1, min(args.concurrent, args.warmup if args.warmup > 0 else 1))
-    eng = BatchIK(graph, device=dev)
-    engs = [eng] + [BatchIK(plan=eng.plan, device=dev) for _ in range(C - 1)]   # one work counter per slot
+    C = max(1, args.concurrent)              # batches in flight (one CUDA stream + work counter each)
+    eng = BatchIK(graph, params={"kernel": args.kernel}, device=dev)
+    engs = [eng] + [BatchIK(plan=eng.plan, params={"kernel": args.kernel}, device=dev) for _ in range(C - 1)]   # one work counter per slot
     streams = [torch.cuda.Stream(device=dev) for _ in range(C)]
     B, N, n = args.batch, graph.number_of_nodes(), robot.n
-    total_steps = args.warmup + args.steps
+    n_warm = max(args.warmup, C)             # every slot/stream is warmed at least once (untimed)
+    total_steps = n_warm + args.steps
     # a different goal set per step and per rank; all resident in HBM before the timed region
     T_host = [goals_for(robot, B, seed=1000 + s + 7919 * rank)[1] for s in range(total_steps)]
     T_dev = [torch.as_tensor(T, device=dev).contiguous() for T in T_host]
@@ -248,7 +250,7 @@ def main():
     # ------------------------------------------------ warm-up = serial steps (one batch at a time);
     # their device time is reported as `serial` (per-batch latency view of the same workload)
     serial_ms = []
-    for s in range(args.warmup):
+    for s in range(n_warm):
         c = s % C
         with torch.cuda.stream(streams[c]):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -275,7 +277,7 @@ def main():
             flush.zero_() if C == 1 else None      # L2 flush between serial steps; with C > 1 the
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()                              # concurrent batches evict each other's lines
-            out, k0, k1 = device_step(engs[c], T_dev[args.warmup + s])
+            out, k0, k1 = device_step(engs[c], T_dev[n_warm + s])
             e1.record()
         outs.append(out)
         ev_rtr.append((k0, k1))
@@ -314,7 +316,7 @@ def main():
     from graphik_b200.solvers.riemannian_solver import RiemannianSolver
     solvers = []
     for e in engs:
-        sv = RiemannianSolver(graph)
+        sv = RiemannianSolver(graph, {"kernel": args.kernel})
         sv._engine = e
         solvers.append(sv)
     h_out = [(torch.empty((B, n), dtype=torch.float64).pin_memory(), torch.empty((B,), dtype=torch.float64).pin_memory(),
@@ -329,12 +331,12 @@ def main():
             h_out[c][1].copy_(o["f(x)"], non_blocking=True)
             h_out[c][2].copy_(o["status"], non_blocking=True)
 
-    for s in range(min(args.warmup, 2)):
+    for s in range(C):
         e2e_step(s, s % C)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        e2e_step(args.warmup + s, s % C)
+        e2e_step(n_warm + s, s % C)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -348,7 +350,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        _, Tc = goals_for(robot, args.cpu_sample, seed=1000 + args.warmup)
+        _, Tc = goals_for(robot, args.cpu_sample, seed=1000 + n_warm)
         cpu_port_solve(robot, graph, Tc[:16], cores)       # warm the OpenMP pool / page in numpy
         dt, res = cpu_port_solve(robot, graph, Tc, cores)
         cpu = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -359,12 +361,13 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "warmup_actual": n_warm, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s ProblemGraphRevolute, batch=%d random reachable goal poses per GPU, "
                                    "no obstacles (BASELINE configs[1])" % (args.robot, B),
                        "robot": args.robot, "batch_per_gpu": B, "nodes": N, "cost_terms": eng.plan.n_terms,
-                       "concurrent_batches": C,
+                       "concurrent_batches": C, "rtr_kernel": args.kernel,
                        "l2": ("flushed between timed steps (256 MiB write)" if C == 1 else
                               "not flushed: %d batches in flight on separate streams evict each other" % C),
                        "parallelism": "goals sharded, dp%d" % world},

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libgraphik_b200.so")
-SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_bounds_init.cu", "gik_joints.cu"]
+SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_bounds_init.cu", "gik_joints.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared", "-cudart", "static"]
 
@@ -73,6 +73,7 @@ class SolveOpts(ctypes.Structure):
         ("rho_prime", ctypes.c_double), ("rho_regularization", ctypes.c_double),
         ("mininner", ctypes.c_int32), ("maxinner", ctypes.c_int32),
         ("Delta_bar", ctypes.c_double), ("Delta0", ctypes.c_double),
+        ("kernel", ctypes.c_int32),
     ]
 
 
@@ -80,7 +81,7 @@ class SolveOpts(ctypes.Structure):
 EXPORTS = [
     "gik_last_error", "gik_version", "gik_default_opts", "gik_plan_create", "gik_plan_destroy",
     "gik_plan_info", "gik_goal_distances", "gik_cost_grad", "gik_hessvec", "gik_proj", "gik_bounds",
-    "gik_init", "gik_bounds_init", "gik_rtr_solve", "gik_joints", "gik_fk",
+    "gik_init", "gik_bounds_init", "gik_rtr_solve", "gik_joints", "gik_fk", "gik_check_limits",
 ]
 
 _lib = None
@@ -91,7 +92,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
+    override = os.environ.get("GRAPHIK_B200_LIB")   # experiments: load an alternative build of the same ABI
+    if override:
+        global LIBPATH
+        LIBPATH = override
+    elif needs_build():
         try:
             build()
         except (GikError, OSError) as e:
@@ -122,6 +127,7 @@ def load():
         "gik_rtr_solve": [vp, vp, vp, i32, ctypes.POINTER(SolveOpts), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
         "gik_joints": [vp, vp, vp, i32, vp, vp],
         "gik_fk": [vp, vp, i32, vp, vp, vp],
+        "gik_check_limits": [vp, vp, dbl, i32, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -44,6 +44,7 @@ extern "C" int gik_default_opts(GikSolveOpts *o)
     o->maxinner = 10000;             // :118
     o->Delta_bar = 13.0;             // fixed_rank_psd_sym.py:72 (10 + k)
     o->Delta0 = 13.0 / 8;            // trust_region.py:137-138
+    o->kernel = GIK_KERNEL_AUTO;
     return GIK_OK;
 }
 
@@ -180,6 +181,22 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         }
     }
 
+    std::vector<uint32_t> dinfo;
+    std::vector<double> dtarget;
+    if (N <= 16 && maxdeg <= GIK_FAST_ROWS) {
+        dinfo.assign((size_t)GIK_FAST_ROWS * 16, 0u);
+        dtarget.assign((size_t)GIK_FAST_ROWS * 16, 0.0);
+        for (int node = 0; node < 16; ++node)
+            for (int s = 0; s < GIK_FAST_ROWS; ++s) {
+                if (node < N && s < deg[node]) {
+                    dinfo[(size_t)s * 16 + node] = info[(size_t)s * N + node];
+                    dtarget[(size_t)s * 16 + node] = target[(size_t)s * N + node];
+                } else {
+                    dinfo[(size_t)s * 16 + node] = (uint32_t)(node < N ? node : 0) | (3u << 16);
+                }
+            }
+    }
+
     // omega edge list for the initialisation's linear projection
     std::vector<int32_t> oi, oj;
     if (d->omega)
@@ -233,6 +250,8 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->deg, deg.data(), deg.size());
     ok = ok && !upload(&p->fast_info, finfo.data(), finfo.size());
     ok = ok && !upload(&p->fast_target, ftarget.data(), ftarget.size());
+    ok = ok && !upload(&p->duo_info, dinfo.data(), dinfo.size());
+    ok = ok && !upload(&p->duo_target, dtarget.data(), dtarget.size());
     ok = ok && !upload(&p->anchor_node, d->anchor_node, (size_t)d->n_anchor);
     ok = ok && !upload(&p->anchor_pos, d->anchor_pos, (size_t)d->n_anchor * 3);
     if (d->bs_lower && d->bs_upper) {
@@ -257,7 +276,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->duo_info, p->duo_target, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};
     for (void *q : ptrs)

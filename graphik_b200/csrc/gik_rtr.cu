@@ -401,10 +401,17 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
     a.Y_out = Y_out; a.f = f; a.gradnorm = gradnorm; a.iters = iters; a.status = status; a.n_inner = n_inner;
     a.trace = trace; a.trace_rows = trace ? trace_rows : 0; a.work_counter = work_counter;
     cudaStream_t st = (cudaStream_t)stream;
-    // N <= 32: one warp per problem with the slot cache in registers (gik_rtr_fast.cu);
-    // GIK_RTR_GENERIC=1 forces the generic group kernel (A/B measurements, tests)
+    // implementation choice (all three run the same algorithm): GIK_RTR_GENERIC=1 / opts->kernel
+    int kernel = a.o.kernel;
     const char *force = getenv("GIK_RTR_GENERIC");
-    if (!(force && force[0] == '1')) {
+    if (force && force[0] == '1') kernel = GIK_KERNEL_GENERIC;
+    if (kernel == GIK_KERNEL_AUTO) kernel = (B >= 16384 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
+    if (kernel == GIK_KERNEL_THROUGHPUT) {
+        const int rc = gik_launch_rtr_duo(p, a, st);
+        if (rc <= 0) return rc;
+        kernel = GIK_KERNEL_LATENCY;   // no lock-step specialisation for this plan
+    }
+    if (kernel == GIK_KERNEL_LATENCY) {
         const int rc = gik_launch_rtr_fast(p, a, st);
         if (rc <= 0) return rc;
     }

@@ -359,19 +359,11 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
     }
 }
 
-// Two register budgets of the same body: the default lets ptxas keep the whole slot cache in
-// registers (best single-problem latency); the OCC variant caps registers at 128 for 16 warps per SM
-// (a few spills, more problems resident) -- chosen for large batches, see launch().
+// register budget: 168 (12 warps / SM) holds the slot cache of the paired layout without spills;
+// the one-lane-per-node layouts (up to 12 slots per lane) get 255
 template <int LPN, int SPL>
-__global__ void __launch_bounds__(kThreads) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
-                                                       const double *__restrict__ fast_target)
-{
-    rtr_fast_body<LPN, SPL>(a, fast_info, fast_target);
-}
-
-template <int LPN, int SPL>
-__global__ void __launch_bounds__(kThreads, 16) k_rtr_fast_occ(const RtrArgs a, const uint32_t *__restrict__ fast_info,
-                                                               const double *__restrict__ fast_target)
+__global__ void __launch_bounds__(kThreads, (LPN == 2 && SPL <= 6) ? 12 : 8) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
+                                                           const double *__restrict__ fast_target)
 {
     rtr_fast_body<LPN, SPL>(a, fast_info, fast_target);
 }
@@ -379,9 +371,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_rtr_fast_occ(const RtrArgs a, 
 template <int LPN, int SPL>
 int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
-    const char *occ_env = getenv("GIK_RTR_OCC");
-    const bool occ = occ_env && occ_env[0] == '1';
-    auto kern = occ ? k_rtr_fast_occ<LPN, SPL> : k_rtr_fast<LPN, SPL>;
+    auto kern = k_rtr_fast<LPN, SPL>;
     constexpr int NPW = 32 / LPN;
     const int goal_pad = (p->n_goal + 1) & ~1;
     const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32) * sizeof(double);

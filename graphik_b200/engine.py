@@ -36,6 +36,8 @@ def make_opts(params=None):
     for key in ("maxiter", "mininner", "maxinner"):
         if key in params:
             setattr(o, key, int(params[key]))
+    if "kernel" in params:   # "auto" | "latency" | "throughput" | "generic" (same results, different SM mapping)
+        o.kernel = {"auto": 0, "latency": 1, "throughput": 2, "generic": 3}[params["kernel"]]
     if "Delta_bar" in params and "Delta0" not in params:
         o.Delta0 = o.Delta_bar / 8  # trust_region.py:137-138
     return o
@@ -202,6 +204,18 @@ class BatchIK:
         self.launches += 1
         return T, Y
 
+    def check_limits(self, Y, tol=1e-6):
+        """Intended-semantics check_distance_limits on the device: violations per problem."""
+        N = self.plan.N
+        Y = self._f64(Y).reshape(-1, N, 3)
+        B = Y.shape[0]
+        out = self._empty(B, dtype=self.torch.int32)
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.gik_check_limits(self.plan.handle, _p(Y), float(tol), B, _p(out), self._stream()),
+                       "gik_check_limits")
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ pipeline
     def solve(self, T_goal, Y_init=None, trace_rows=0, check=True):
         """solve_with_riemannian for a batch of goal poses T_goal[B,4,4] (device or host).
@@ -216,7 +230,8 @@ class BatchIK:
         out["goal_d2"] = g2
         out["q"] = self.joints(out["x"], T)
         if check:
-            T_sol, _ = self.fk(out["q"], want_points=False)
+            T_sol, Y_real = self.fk(out["q"], want_points=True)
+            out["n_broken"] = self.check_limits(Y_real, tol=1e-6)   # riemannian_solver.py:230 (intended semantics)
             out["pos_err"] = (T_sol[:, :3, 3] - T[:, :3, 3]).norm(dim=1)
             R = T_sol[:, :3, :3].transpose(1, 2) @ T[:, :3, :3]
             cosang = ((R.diagonal(dim1=1, dim2=2).sum(1) - 1.0) * 0.5).clamp(-1.0, 1.0)

@@ -104,16 +104,24 @@ class RiemannianSolver:
         return out
 
 
-def solve_with_riemannian(graph, T_goal, use_jit=True, jit=None):
-    """riemannian_solver.py:220-234: (q_sol dict, points[N,3]) or (None, None)."""
+def solve_with_riemannian(graph, T_goal, use_jit=True, jit=None, limit_semantics="reference"):
+    """riemannian_solver.py:220-234: (q_sol dict, points[N,3]) or (None, None).
+
+    limit_semantics="reference" reproduces the reference as shipped, whose check_distance_limits never
+    reports a violation on revolute graphs (graph_base.py:226-258 compares a list with a string), so a
+    solution is always returned; "intended" runs the limit check (on the device) and returns (None, None)
+    when a joint-limit or obstacle distance bound is broken by more than 1e-6."""
     solver = RiemannianSolver(graph)
     T = as_matrix4(T_goal)
-    out = solver.solve_batch(T[None], check=False)
+    out = solver.solve_batch(T[None], check=(limit_semantics == "intended"))
     Y = out["x"][0].cpu().numpy()
     q = out["q"][0].cpu().numpy()
     q_sol = graph.robot.q_dict(q)
-    broken_limits = graph.check_distance_limits(graph.realization(q_sol), tol=1e-6)
-    if len(broken_limits) > 0:
+    if limit_semantics == "intended":
+        n_broken = int(out["n_broken"][0])
+    else:
+        n_broken = len(graph.check_distance_limits(graph.realization(q_sol), tol=1e-6))
+    if n_broken > 0:
         return None, None
     return q_sol, Y
 

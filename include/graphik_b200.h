@@ -100,7 +100,14 @@ typedef struct {
     int32_t maxinner;           /* 10000 */
     double Delta_bar;           /* 13 = typicaldist = 10 + k */
     double Delta0;              /* Delta_bar / 8 */
+    int32_t kernel;             /* GIK_KERNEL_*: which implementation gik_rtr_solve launches (same results) */
 } GikSolveOpts;
+
+/* gik_rtr_solve implementations (identical algorithm, different mapping to the SM) */
+#define GIK_KERNEL_AUTO 0        /* latency kernel for small batches, throughput kernel for B >= 16384 */
+#define GIK_KERNEL_LATENCY 1     /* one warp per problem, register slot cache (N <= 32) */
+#define GIK_KERNEL_THROUGHPUT 2  /* two problems per warp in lock-step (N <= 16) */
+#define GIK_KERNEL_GENERIC 3     /* W-lane groups, any N <= 128 */
 
 const char *gik_last_error(void);
 int gik_version(void);
@@ -172,6 +179,13 @@ int gik_joints(const GikPlan *plan, const double *Y, const double *T_goal, int32
  * (robot_revolute.py:85-103, graph_base.py:112-121):
  * q[B][n_joints] -> T_ee[B][4][4] (may be NULL), Y[B][N][3] (may be NULL). */
 int gik_fk(const GikPlan *plan, const double *q, int32_t B, double *T_ee, double *Y, void *stream);
+
+/* ProblemGraph.check_distance_limits (graph_base.py:219-260) with the INTENDED semantics: for every
+ * edge carrying a BELOW/ABOVE limit count the realised distances outside [LOWER - tol, UPPER + tol].
+ * (As shipped, the reference's own node-type test never fires on revolute graphs, so it reports no
+ * violation at all; callers wanting that behaviour simply skip this call.)  Y[B][N][3] -> n_broken[B]. */
+int gik_check_limits(const GikPlan *plan, const double *Y, double tol, int32_t B, int32_t *n_broken,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -151,3 +151,22 @@ def test_joint_variables_and_fk(name):
     assert np.max(np.abs(Y_dev.cpu().numpy() - graph.realization_points(Q))) <= 1e-12
     q_rec = eng.joints(Y_dev, T_dev).cpu().numpy()
     np.testing.assert_allclose(q_rec, Q, rtol=1e-5, atol=1e-9)
+
+
+def test_check_limits_device_vs_host_intended():
+    """gik_check_limits against the host restatement of check_distance_limits with the intended
+    semantics, on realisations that respect / violate a tightened joint limit."""
+    import numpy as np
+    from graphik_b200.engine import BatchIK
+    lim = 0.6 * np.pi * np.ones(6)
+    robot, graph = load_robot("ur10", limits=(-lim, lim))
+    eng = BatchIK(graph)
+    rng = np.random.RandomState(1)
+    Q = -np.pi + 2 * np.pi * rng.rand(200, 6)        # many of these break the +-0.6 pi limits
+    T, Y = eng.fk(Q)
+    dev = eng.check_limits(Y, tol=1e-6).cpu().numpy()
+    host = np.array([len(graph.check_distance_limits(Y[k].cpu().numpy(), tol=1e-6, semantics="intended"))
+                     for k in range(200)])
+    assert np.array_equal(dev, host)
+    assert dev.max() > 0 and (dev == 0).any()
+    assert all(len(graph.check_distance_limits(Y[k].cpu().numpy(), tol=1e-6)) == 0 for k in range(5))  # as shipped

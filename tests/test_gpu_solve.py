@@ -134,21 +134,52 @@ def test_maxiter_and_nan_status():
     assert st[0] == 0 and st[1] == 2   # a NaN problem is flagged and does not poison its neighbour
 
 
-def test_generic_group_kernel_agrees_with_fast_kernel(monkeypatch):
-    """k_rtr (W-lane groups, any N) and k_rtr_fast (one warp per problem, register slot cache) are the
-    same algorithm with different summation orders: identical leading decisions, same end quality."""
+def test_kernel_variants_agree():
+    """gik_rtr_solve has three implementations of the same algorithm -- latency (one warp per problem,
+    register slot cache), throughput (two problems per warp in lock-step) and generic (W-lane groups, any
+    N) -- that differ only in summation order: identical leading decisions, same end quality."""
+    from graphik_b200.engine import make_opts
     robot, graph, eng = _engine("ur10")
     g = golden("ur10_goals")
     K = len(g["f"])
     rows = np.stack([eng.plan.goal_row_from_matrix(g["D_goal"][k]) for k in range(K)])
-    fast = eng.solve_points(rows, g["Y_init"], trace_rows=32)
-    monkeypatch.setenv("GIK_RTR_GENERIC", "1")
-    gen = eng.solve_points(rows, g["Y_init"], trace_rows=32)
-    monkeypatch.delenv("GIK_RTR_GENERIC")
-    tf, tg = fast["trace"].cpu().numpy(), gen["trace"].cpu().numpy()
-    for k in range(K):
-        assert np.array_equal(tf[k, :6][:, [1, 2, 4]], tg[k, :6][:, [1, 2, 4]]), (k, tf[k, :6], tg[k, :6])
-        np.testing.assert_allclose(tf[k, :6, 3], tg[k, :6, 3], rtol=1e-6)
-    for out in (fast, gen):
-        assert np.all(out["f(x)"].cpu().numpy() < 1e-11)
-        assert np.all(out["gradnorm"].cpu().numpy() < 5e-10)
+    outs = {name: eng.solve_points(rows, g["Y_init"], trace_rows=32, opts=make_opts({"kernel": name}))
+            for name in ("latency", "throughput", "generic")}
+    tf = outs["latency"]["trace"].cpu().numpy()
+    for name in ("throughput", "generic"):
+        tg = outs[name]["trace"].cpu().numpy()
+        for k in range(K):
+            assert np.array_equal(tf[k, :6][:, [1, 2, 4]], tg[k, :6][:, [1, 2, 4]]), (name, k, tf[k, :6], tg[k, :6])
+            np.testing.assert_allclose(tf[k, :6, 3], tg[k, :6, 3], rtol=1e-6)
+    for name, out in outs.items():
+        assert np.all(out["f(x)"].cpu().numpy() < 1e-11), name
+        assert np.all(out["gradnorm"].cpu().numpy() < 5e-10), name
+        assert np.all(out["status"].cpu().numpy() == 0), name
+
+
+def test_throughput_kernel_statistics_and_independence():
+    """Lock-step kernel on a ragged batch (odd size, so one half-warp idles at the end): same statistics as
+    the latency kernel, bit-identical results whatever problem shares the warp."""
+    from graphik_b200.engine import make_opts
+    robot, graph, eng = _engine("ur10")
+    Q, T = random_goals(robot, 301, seed=11)
+    gd = eng.goal_distances(T)
+    Y0 = eng.initialization(gd)
+    thr = eng.solve_points(gd, Y0, opts=make_opts({"kernel": "throughput"}))
+    lat = eng.solve_points(gd, Y0, opts=make_opts({"kernel": "latency"}))
+    perm = np.random.RandomState(0).permutation(301)
+    import torch
+    pt = torch.as_tensor(perm, device=gd.device)
+    thr2 = eng.solve_points(gd[pt].contiguous(), Y0[pt].contiguous(), opts=make_opts({"kernel": "throughput"}))
+    for key in ("x", "f(x)", "gradnorm", "iterations", "n_inner"):
+        assert np.array_equal(thr[key].cpu().numpy()[perm], thr2[key].cpu().numpy()), key
+    it_t, it_l = thr["iterations"].cpu().numpy(), lat["iterations"].cpu().numpy()
+    assert 0.8 < np.median(it_t) / np.median(it_l) < 1.25
+    assert np.median(thr["f(x)"].cpu().numpy()) < 1e-13
+    assert abs(np.mean(thr["status"].cpu().numpy() == 0) - np.mean(lat["status"].cpu().numpy() == 0)) < 0.03
+    # NaN input does not disturb the problem sharing its warp
+    Yn = Y0[:2].clone()
+    Yn[0, 3, 1] = float("nan")
+    o = eng.solve_points(gd[:2], Yn, opts=make_opts({"kernel": "throughput"}))
+    assert o["status"].cpu().numpy().tolist() == [2, 0]
+    assert np.array_equal(o["x"][1].cpu().numpy(), thr["x"][1].cpu().numpy())
