@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="goals per step of the CPU arm / cpu_baseline")
     ap.add_argument("--concurrent", type=int, default=8,
                     help="batches in flight (CUDA streams); 1 = strictly one batch at a time")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "latency", "throughput", "generic"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "latency", "throughput", "generic", "dense"],
                     help="gik_rtr_solve implementation (same results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

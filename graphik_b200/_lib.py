@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libgraphik_b200.so")
-SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_bounds_init.cu", "gik_joints.cu"]
+SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_rtr_cta.cu", "gik_bounds_init.cu", "gik_joints.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--shared", "-cudart", "static"]
 

@@ -197,6 +197,26 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
             }
     }
 
+    // dense pair tables for k_rtr_cta
+    std::vector<double> dense_t;
+    std::vector<unsigned char> dense_k;
+    std::vector<int32_t> dgi, dgj, dgs;
+    if (N > 32 && N <= 128) {
+        dense_t.assign((size_t)N * N, 0.0);
+        dense_k.assign((size_t)N * N, 3);
+        bool representable = true;
+        for (int t = 0; t < d->n_terms && representable; ++t) {
+            const int i = d->term_i[t], j = d->term_j[t];
+            if (dense_k[(size_t)i * N + j] != 3) { representable = false; break; }   // two terms on one pair
+            dense_k[(size_t)i * N + j] = dense_k[(size_t)j * N + i] = (unsigned char)d->term_kind[t];
+            dense_t[(size_t)i * N + j] = dense_t[(size_t)j * N + i] = d->term_target[t];
+            const int gs = d->term_goal ? d->term_goal[t] : -1;
+            if (gs >= 0) { dgi.push_back(i); dgj.push_back(j); dgs.push_back(gs); }
+        }
+        if (!representable) { dense_t.clear(); dense_k.clear(); dgi.clear(); dgj.clear(); dgs.clear(); }
+    }
+    p->n_dense_goal = (int)dgi.size();
+
     // omega edge list for the initialisation's linear projection
     std::vector<int32_t> oi, oj;
     if (d->omega)
@@ -252,6 +272,11 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->fast_target, ftarget.data(), ftarget.size());
     ok = ok && !upload(&p->duo_info, dinfo.data(), dinfo.size());
     ok = ok && !upload(&p->duo_target, dtarget.data(), dtarget.size());
+    ok = ok && !upload(&p->dense_target, dense_t.data(), dense_t.size());
+    ok = ok && !upload(&p->dense_kind, dense_k.data(), dense_k.size());
+    ok = ok && !upload(&p->dense_goal_i, dgi.data(), dgi.size());
+    ok = ok && !upload(&p->dense_goal_j, dgj.data(), dgj.size());
+    ok = ok && !upload(&p->dense_goal_slot, dgs.data(), dgs.size());
     ok = ok && !upload(&p->anchor_node, d->anchor_node, (size_t)d->n_anchor);
     ok = ok && !upload(&p->anchor_pos, d->anchor_pos, (size_t)d->n_anchor * 3);
     if (d->bs_lower && d->bs_upper) {
@@ -276,7 +301,8 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->duo_info, p->duo_target, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_goal_i, p->dense_goal_j,
+                    p->dense_goal_slot, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};
     for (void *q : ptrs)

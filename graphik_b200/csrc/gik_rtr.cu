@@ -405,7 +405,15 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
     int kernel = a.o.kernel;
     const char *force = getenv("GIK_RTR_GENERIC");
     if (force && force[0] == '1') kernel = GIK_KERNEL_GENERIC;
-    if (kernel == GIK_KERNEL_AUTO) kernel = (B >= 16384 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
+    if (kernel == GIK_KERNEL_AUTO) {
+        if (p->N <= 32) kernel = (B >= 16384 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
+        else kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE : GIK_KERNEL_GENERIC;
+    }
+    if (kernel == GIK_KERNEL_DENSE) {
+        const int rc = gik_launch_rtr_cta(p, a, st);
+        if (rc <= 0) return rc;
+        kernel = GIK_KERNEL_GENERIC;
+    }
     if (kernel == GIK_KERNEL_THROUGHPUT) {
         const int rc = gik_launch_rtr_duo(p, a, st);
         if (rc <= 0) return rc;

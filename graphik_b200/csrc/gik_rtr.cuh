@@ -27,3 +27,5 @@ struct RtrArgs {
 int gik_launch_rtr_fast(const GikPlan *p, RtrArgs &a, cudaStream_t st);
 // gik_rtr_duo.cu: two problems per warp in lock-step (N <= 16); same return convention.
 int gik_launch_rtr_duo(const GikPlan *p, RtrArgs &a, cudaStream_t st);
+// gik_rtr_cta.cu: one CTA per problem with a dense target matrix (32 < N <= 128); same convention.
+int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st);

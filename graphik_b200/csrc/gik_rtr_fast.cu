@@ -94,7 +94,11 @@ struct SlotCache {
     double c2;          // 2 * act * (d_ij - T_ij)
 };
 
-template <int LPN, int SPL>
+// SMC: keep the slot cache in shared memory ([slot][4][lane], conflict-free) instead of registers --
+// used for the one-lane-per-node layouts (17..32 nodes, up to 12 slots per lane), where the register
+// cache costs 238+ registers (8 warps / SM); the loads do not depend on delta, so they stay off the
+// critical path
+template <int LPN, int SPL, bool SMC>
 __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *__restrict__ fast_info,
                                               const double *__restrict__ fast_target)
 {
@@ -105,10 +109,11 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
     const int node = lane / LPN;
     const bool valid = node < a.N;
     const int goal_pad = (a.n_goal + 1) & ~1;
-    double *P = smem + (size_t)warp * (6 * NPW + goal_pad + SPL * 32);
+    double *P = smem + (size_t)warp * (6 * NPW + goal_pad + SPL * 32 + (SMC ? SPL * 128 : 0));
     double *V = P + 3 * NPW;
     double *goal = V + 3 * NPW;
     double *tgt = goal + goal_pad + lane;   // [SPL][32] per-problem targets of this warp's slots
+    double *scm = tgt + SPL * 32;           // [SPL][4][32] slot cache when SMC
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
 
@@ -124,7 +129,7 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
         if (b >= a.B) break;
 
         double x[3] = {0.0, 0.0, 0.0}, g[3], eta[3], Heta[3], r[3], dl[3], Hd[3];
-        SlotCache sc[SPL];
+        SlotCache sc[SMC ? 1 : SPL];
         if (valid) {
             const double *src = a.Y_init + ((size_t)b * a.N + node) * 3;
             x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
@@ -158,8 +163,13 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
                 gy = fma(rr, dy, gy);
                 gz = fma(rr, dz, gz);
                 const double two = act ? 2.0 : 0.0;
-                sc[s].dx = two * dx; sc[s].dy = two * dy; sc[s].dz = two * dz;
-                sc[s].c2 = 2.0 * rr;
+                if (SMC) {
+                    scm[(s * 4 + 0) * 32] = two * dx; scm[(s * 4 + 1) * 32] = two * dy;
+                    scm[(s * 4 + 2) * 32] = two * dz; scm[(s * 4 + 3) * 32] = 2.0 * rr;
+                } else {
+                    sc[s].dx = two * dx; sc[s].dy = two * dy; sc[s].dz = two * dz;
+                    sc[s].c2 = 2.0 * rr;
+                }
             }
             double v[3] = {2.0 * gx, 2.0 * gy, 2.0 * gz};
             pair_combine<LPN, 3>(v);
@@ -211,13 +221,17 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
                     for (int s = 0; s < SPL; ++s) {
                         const int jn = GIK_SLOT_NBR(info[s]);
                         const double wx = dl[0] - V[jn], wy = dl[1] - V[NPW + jn], wz = dl[2] - V[2 * NPW + jn];
-                        const double t = fma(sc[s].dx, wx, fma(sc[s].dy, wy, sc[s].dz * wz));
-                        z[0] = fma(sc[s].c2, wx, z[0]);
-                        z[1] = fma(sc[s].c2, wy, z[1]);
-                        z[2] = fma(sc[s].c2, wz, z[2]);
-                        zb[0] = fma(t, sc[s].dx, zb[0]);
-                        zb[1] = fma(t, sc[s].dy, zb[1]);
-                        zb[2] = fma(t, sc[s].dz, zb[2]);
+                        const double cx = SMC ? scm[(s * 4 + 0) * 32] : sc[s].dx;
+                        const double cy = SMC ? scm[(s * 4 + 1) * 32] : sc[s].dy;
+                        const double cz = SMC ? scm[(s * 4 + 2) * 32] : sc[s].dz;
+                        const double c2 = SMC ? scm[(s * 4 + 3) * 32] : sc[s].c2;
+                        const double t = fma(cx, wx, fma(cy, wy, cz * wz));
+                        z[0] = fma(c2, wx, z[0]);
+                        z[1] = fma(c2, wy, z[1]);
+                        z[2] = fma(c2, wz, z[2]);
+                        zb[0] = fma(t, cx, zb[0]);
+                        zb[1] = fma(t, cy, zb[1]);
+                        zb[2] = fma(t, cz, zb[2]);
                     }
                     z[0] += zb[0]; z[1] += zb[1]; z[2] += zb[2];
                     pair_combine<LPN, 3>(z);
@@ -360,12 +374,12 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
 }
 
 // register budget: 168 (12 warps / SM) holds the slot cache of the paired layout without spills;
-// the one-lane-per-node layouts (up to 12 slots per lane) get 255
+// the one-lane-per-node layouts keep it in shared memory and get the same budget
 template <int LPN, int SPL>
-__global__ void __launch_bounds__(kThreads, (LPN == 2 && SPL <= 6) ? 12 : 8) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
+__global__ void __launch_bounds__(kThreads, 12) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
                                                            const double *__restrict__ fast_target)
 {
-    rtr_fast_body<LPN, SPL>(a, fast_info, fast_target);
+    rtr_fast_body<LPN, SPL, (LPN == 1 || SPL > 6)>(a, fast_info, fast_target);
 }
 
 template <int LPN, int SPL>
@@ -373,8 +387,9 @@ int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
     auto kern = k_rtr_fast<LPN, SPL>;
     constexpr int NPW = 32 / LPN;
+    constexpr bool SMC = (LPN == 1 || SPL > 6);
     const int goal_pad = (p->n_goal + 1) & ~1;
-    const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32) * sizeof(double);
+    const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32 + (SMC ? SPL * 128 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
         GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -36,8 +36,8 @@ def make_opts(params=None):
     for key in ("maxiter", "mininner", "maxinner"):
         if key in params:
             setattr(o, key, int(params[key]))
-    if "kernel" in params:   # "auto" | "latency" | "throughput" | "generic" (same results, different SM mapping)
-        o.kernel = {"auto": 0, "latency": 1, "throughput": 2, "generic": 3}[params["kernel"]]
+    if "kernel" in params:   # "auto" | "latency" | "throughput" | "generic" | "dense" (same results, different SM mapping)
+        o.kernel = {"auto": 0, "latency": 1, "throughput": 2, "generic": 3, "dense": 4}[params["kernel"]]
     if "Delta_bar" in params and "Delta0" not in params:
         o.Delta0 = o.Delta_bar / 8  # trust_region.py:137-138
     return o

@@ -48,13 +48,18 @@ def test_kuka_table_pipeline_vs_reference():
     # trust-region solve from the reference's own starting point (bounded: the reference needs up to
     # 2600 outer iterations here) -- leading decisions against the oracle, then quality
     from graphik_b200.engine import make_opts
-    out = eng.solve_points(rows, g["Y_init"], trace_rows=16, opts=make_opts({"maxiter": 400}))
-    tr = out["trace"].cpu().numpy()
-    for k in range(K):
-        P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
-        ref = P.solve(g["Y_init"][k], params={"maxiter": 16}, trace_rows=16)["trace"]
-        m = min(len(ref), 4)
-        assert np.array_equal(tr[k, :m][:, [1, 2, 4]], ref[:m][:, [1, 2, 4]]), (k, tr[k, :m], ref[:m])
-        np.testing.assert_allclose(tr[k, :m, 3], ref[:m, 3], rtol=1e-6)
-    f_end = out["f(x)"].cpu().numpy()
-    assert np.all(f_end < 1e-3 * g["f0"]), (f_end, g["f0"])
+    for kernel in ("dense", "generic"):   # CTA-per-problem dense kernel (the AUTO choice here) and W-lane groups
+        out = eng.solve_points(rows, g["Y_init"], trace_rows=16, opts=make_opts({"maxiter": 400, "kernel": kernel}))
+        tr = out["trace"].cpu().numpy()
+        for k in range(K):
+            P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
+            ref = P.solve(g["Y_init"][k], params={"maxiter": 16}, trace_rows=16)["trace"]
+            m = min(len(ref), 4)
+            assert np.array_equal(tr[k, :m][:, [1, 2, 4]], ref[:m][:, [1, 2, 4]]), (kernel, k, tr[k, :m], ref[:m])
+            np.testing.assert_allclose(tr[k, :m, 3], ref[:m, 3], rtol=1e-6)
+        f_end = out["f(x)"].cpu().numpy()
+        assert np.all(f_end < 1e-3 * g["f0"]), (kernel, f_end, g["f0"])
+        x, f = out["x"].cpu().numpy(), out["f(x)"].cpu().numpy()
+        for k in range(K):   # reported cost == lcost of the returned points
+            P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
+            assert abs(P.cost(x[k]) - f[k]) <= 1e-11 * max(1.0, f[k])
