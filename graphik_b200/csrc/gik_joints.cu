@@ -228,8 +228,9 @@ extern "C" int gik_check_limits(const GikPlan *p, const double *Y, double tol, i
 extern "C" int gik_joints(const GikPlan *p, const double *Y, const double *T_goal, int32_t B, double *q, void *stream)
 {
     if (B == 0) return GIK_OK;
-    if (!p || !Y || !q || B < 0) { gik_set_error("gik_joints: bad argument"); return GIK_EINVAL; }
+    if (!p) { gik_set_error("gik_joints: null plan"); return GIK_EINVAL; }
     if (p->n_joints <= 0 || !p->T0) { gik_set_error("gik_joints: plan was created without joint tables"); return GIK_EINVAL; }
+    if (!Y || !q || B < 0) { gik_set_error("gik_joints: bad argument"); return GIK_EINVAL; }
     if (p->N < 4 + 2 * p->n_joints) { gik_set_error("gik_joints: node layout does not match n_joints"); return GIK_EINVAL; }
     if (B == 0) return GIK_OK;
     k_joints<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->N, p->n_joints, p->T0, p->Trel, p->qs0,
@@ -240,8 +241,9 @@ extern "C" int gik_joints(const GikPlan *p, const double *Y, const double *T_goa
 extern "C" int gik_fk(const GikPlan *p, const double *q, int32_t B, double *T_ee, double *Y, void *stream)
 {
     if (B == 0) return GIK_OK;
-    if (!p || !q || B < 0) { gik_set_error("gik_fk: bad argument"); return GIK_EINVAL; }
+    if (!p) { gik_set_error("gik_fk: null plan"); return GIK_EINVAL; }
     if (p->n_joints <= 0 || !p->T0) { gik_set_error("gik_fk: plan was created without joint tables"); return GIK_EINVAL; }
+    if (!q || B < 0) { gik_set_error("gik_fk: bad argument"); return GIK_EINVAL; }
     if (B == 0 || (!T_ee && !Y)) return GIK_OK;
     k_fk<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->N, p->n_joints, p->n_anchor, p->anchor_node,
                                                           p->anchor_pos, p->axis_length, p->T0, q, B, T_ee, Y);

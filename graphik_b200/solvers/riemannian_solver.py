@@ -117,10 +117,9 @@ def solve_with_riemannian(graph, T_goal, use_jit=True, jit=None, limit_semantics
     Y = out["x"][0].cpu().numpy()
     q = out["q"][0].cpu().numpy()
     q_sol = graph.robot.q_dict(q)
-    if limit_semantics == "intended":
-        n_broken = int(out["n_broken"][0])
-    else:
-        n_broken = len(graph.check_distance_limits(graph.realization(q_sol), tol=1e-6))
+    # "reference": riemannian_solver.py:230 calls check_distance_limits, which (as shipped) returns []
+    # for every revolute graph -- nothing to evaluate
+    n_broken = int(out["n_broken"][0]) if limit_semantics == "intended" else 0
     if n_broken > 0:
         return None, None
     return q_sol, Y

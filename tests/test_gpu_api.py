@@ -102,3 +102,44 @@ def test_multi_gpu_sharding_is_exact():
     with torch.cuda.device(1):
         part = BatchIK(graph, device=1).solve(T[32:], check=False)
     assert np.array_equal(full["x"][32:].cpu().numpy(), part["x"].cpu().numpy())
+
+
+def test_c_abi_error_codes_and_empty_batches():
+    """Every entry point: B = 0 is a no-op, bad arguments / limits come back as negative codes with a
+    message, nothing throws across the ABI."""
+    import ctypes
+    import torch
+    from graphik_b200 import _lib
+    from graphik_b200.engine import BatchIK
+    from graphik_b200.plan import Plan
+    robot, graph = load_robot("ur10")
+    eng = BatchIK(graph)
+    L, h = eng.lib, eng.plan.handle
+    null = ctypes.c_void_p(0)
+    assert L.gik_goal_distances(h, null, 0, null, null) == 0
+    assert L.gik_cost_grad(h, null, null, 0, null, null, null) == 0
+    assert L.gik_hessvec(h, null, null, null, 0, null, null) == 0
+    assert L.gik_proj(16, null, null, 0, null, null) == 0
+    assert L.gik_bounds(h, null, 0, null, null, null) == 0
+    assert L.gik_init(h, null, null, 0, null, null) == 0
+    assert L.gik_bounds_init(h, null, 0, null, null) == 0
+    assert L.gik_joints(h, null, null, 0, null, null) == 0
+    assert L.gik_fk(h, null, 0, null, null, null) == 0
+    assert L.gik_check_limits(h, null, 1e-6, 0, null, null) == 0
+    assert L.gik_rtr_solve(h, null, null, 0, None, null, null, null, null, null, null, null, 0, null, null) == 0
+    # null pointers with B > 0 -> GIK_EINVAL (-1) and a message
+    assert L.gik_cost_grad(h, null, null, 4, null, null, null) == -1
+    assert b"gik_cost_grad" in L.gik_last_error()
+    assert L.gik_rtr_solve(h, null, null, 4, None, null, null, null, null, null, null, null, 0, null, null) == -1
+    assert L.gik_proj(1, null, null, 4, null, null) == -1
+    # more nodes than any kernel is compiled for -> GIK_ELIMIT (-3) at plan creation
+    N = 200
+    with pytest.raises(_lib.GikError, match="exceeds the compiled limit"):
+        Plan.from_matrices(np.ones((N, N)), np.triu(np.ones((N, N)), 1))
+    # a plan without joint tables refuses joint recovery instead of reading garbage
+    static = BatchIK(plan=Plan.from_matrices(np.ones((16, 16)), np.triu(np.ones((16, 16)), 1)))
+    with pytest.raises(_lib.GikError, match="without joint tables"):
+        static.joints(np.zeros((1, 16, 3)))
+    # empty batch through the Python engine
+    out = eng.solve(np.zeros((0, 4, 4)), check=False)
+    assert out["q"].shape == (0, 6) and out["x"].shape == (0, 16, 3)
