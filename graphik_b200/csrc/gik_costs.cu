@@ -107,6 +107,93 @@ k_costs(PlanView pv, const double *__restrict__ Y, const double *__restrict__ Wd
     }
 }
 
+// Same operators for N <= 32 with the lane-centric tables of the solver's latency kernel: one warp per
+// problem, LPN lanes per node, the slot description of a lane lives in registers for the whole launch,
+// so a problem costs one coalesced read of Y (and W), the edge pass, and one coalesced write.
+template <int LPN, int SPL, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_costs_fast(int N, int n_goal, const uint32_t *__restrict__ fast_info, const double *__restrict__ fast_target,
+             const double *__restrict__ Y, const double *__restrict__ Wd, const double *__restrict__ goal_d2,
+             int B, double *__restrict__ f, double *__restrict__ out)
+{
+    constexpr int NPW = 32 / LPN;
+    constexpr int WPB = kThreads / 32;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = lane / LPN;
+    const bool valid = node < N, owner = valid && (lane % LPN == 0);
+    const int goal_pad = (n_goal + 1) & ~1;
+    double *P = smem + (size_t)warp * (6 * NPW + goal_pad);
+    double *V = P + 3 * NPW;
+    double *goal = V + 3 * NPW;
+    uint32_t info[SPL];
+    double tstat[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+        info[s] = fast_info[s * 32 + lane];
+        tstat[s] = fast_target[s * 32 + lane];
+    }
+    for (int b = blockIdx.x * WPB + warp; b < B; b += gridDim.x * WPB) {
+        double x[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0};
+        if (valid) {
+            const double *src = Y + ((size_t)b * N + node) * 3;
+            x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
+            if (MODE == 1) {
+                const double *sw = Wd + ((size_t)b * N + node) * 3;
+                w[0] = sw[0]; w[1] = sw[1]; w[2] = sw[2];
+            }
+        }
+        for (int k = lane; k < n_goal; k += 32) goal[k] = goal_d2[(size_t)b * n_goal + k];
+        if (lane % LPN == 0) {
+            P[node] = x[0]; P[NPW + node] = x[1]; P[2 * NPW + node] = x[2];
+            if (MODE == 1) { V[node] = w[0]; V[NPW + node] = w[1]; V[2 * NPW + node] = w[2]; }
+        }
+        __syncwarp();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};   // x, y, z of the node sum; cost share
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            const int j = GIK_SLOT_NBR(info[s]);
+            const uint32_t kind = GIK_SLOT_KIND(info[s]);
+            const uint32_t gs = GIK_SLOT_GOAL(info[s]);
+            const double T = gs ? goal[gs - 1] : tstat[s];
+            const double dx = x[0] - P[j], dy = x[1] - P[NPW + j], dz = x[2] - P[2 * NPW + j];
+            const double d = dx * dx + dy * dy + dz * dz;
+            double r = d - T;
+            const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (r < 0.0)) |
+                             ((kind == GIK_TERM_UP) & (r > 0.0));
+            r = act ? r : 0.0;
+            if (MODE == 0) {
+                acc[3] = fma(r, r, acc[3]);
+                acc[0] = fma(r, dx, acc[0]);
+                acc[1] = fma(r, dy, acc[1]);
+                acc[2] = fma(r, dz, acc[2]);
+            } else {
+                const double wx = w[0] - V[j], wy = w[1] - V[NPW + j], wz = w[2] - V[2 * NPW + j];
+                const double a2 = act ? 2.0 * (dx * wx + dy * wy + dz * wz) : 0.0;
+                acc[0] = fma(a2, dx, fma(r, wx, acc[0]));
+                acc[1] = fma(a2, dy, fma(r, wy, acc[1]));
+                acc[2] = fma(a2, dz, fma(r, wz, acc[2]));
+            }
+        }
+#pragma unroll
+        for (int off = LPN / 2; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(GIK_FULL_MASK, acc[k], off, 32);
+        }
+        if (MODE == 0 && f) {
+            double fs = 0.5 * acc[3];          // pairs already combined: count each node once
+#pragma unroll
+            for (int off = 16; off >= LPN; off >>= 1) fs += __shfl_xor_sync(GIK_FULL_MASK, fs, off, 32);
+            if (lane == 0) f[b] = fs;
+        }
+        if (out && owner) {
+            double *dst = out + ((size_t)b * N + node) * 3;
+            dst[0] = 2.0 * acc[0]; dst[1] = 2.0 * acc[1]; dst[2] = 2.0 * acc[2];
+        }
+        __syncwarp();
+    }
+}
+
 // fixed_rank_psd_sym.py:91-113 via the 3x3 form: with X = Y^T Y and c = sum_i Z_i x Y_i,
 // (tr(X) I - X) omega = c and proj(Z)_i = Z_i - Y_i x omega.
 template <int W, int NPL>
@@ -195,10 +282,33 @@ int launch_costs(const GikPlan *p, const double *Y, const double *Wd, const doub
     return gik_check_cuda(cudaGetLastError(), "k_costs launch");
 }
 
+template <int LPN, int SPL, int MODE>
+int launch_costs_fast(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
+                      double *f, double *out, cudaStream_t st)
+{
+    constexpr int NPW = 32 / LPN, WPB = kThreads / 32;
+    const int goal_pad = (p->n_goal + 1) & ~1;
+    const size_t smem = (size_t)WPB * (6 * NPW + goal_pad) * sizeof(double);
+    if (smem > 48 * 1024)
+        GIK_CUDA(cudaFuncSetAttribute(k_costs_fast<LPN, SPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (B + WPB - 1) / WPB;
+    const int cap = p->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_costs_fast<LPN, SPL, MODE><<<blocks, kThreads, smem, st>>>(p->N, p->n_goal, p->fast_info, p->fast_target, Y, Wd,
+                                                                goal_d2, B, f, out);
+    return gik_check_cuda(cudaGetLastError(), "k_costs_fast launch");
+}
+
 template <int MODE>
 int dispatch_costs(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
                    double *f, double *out, cudaStream_t st)
 {
+    // 17..32 nodes: warp per problem with register-resident slot tables (KUKA: 1.4x the group kernel);
+    // N <= 16 stays on the 16-lane groups, which put two problems in a warp (measured faster there)
+    if (p->fast_info && p->fast_LPN == 1) {
+        if (p->fast_SPL <= 9) return launch_costs_fast<1, 9, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        if (p->fast_SPL <= 12) return launch_costs_fast<1, 12, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+    }
     if (p->W == 16) return launch_costs<16, 1, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
     switch (p->NPL) {
         case 1: return launch_costs<32, 1, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
