@@ -22,9 +22,13 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef GIK_CTA_THREADS
+#define GIK_CTA_THREADS 256
+#endif
+constexpr int kThreads = GIK_CTA_THREADS;   // 2 (or 4) threads per node, each owning a slice of the neighbour range
 constexpr int kWarps = kThreads / 32;
 constexpr int NPAD = 128;
+constexpr int kParts = kThreads / NPAD;
 
 template <int K>
 __device__ __forceinline__ void block_allreduce(double (&v)[K], double *red, int warp, int lane)
@@ -64,12 +68,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
     const int node = tid % NPAD, part = tid / NPAD;
     const bool valid = node < N;
     const bool owner = valid && part == 0;
-    const int jlo = part == 0 ? 0 : (N + 1) / 2, jhi = part == 0 ? (N + 1) / 2 : N;
+    const int jchunk = (N + kParts - 1) / kParts;
+    const int jlo = part * jchunk, jhi = min(N, jlo + jchunk);
     double *T = smem;                                   // [N][NPAD]
     double *P = T + (size_t)N * NPAD;                   // [3][NPAD]
     double *V = P + 3 * NPAD;                           // [3][NPAD]
-    double *Zx = V + 3 * NPAD;                          // [2][3][NPAD] partial sums of the two halves
-    double *red = Zx + 6 * NPAD;                        // [kWarps][10]
+    double *Zx = V + 3 * NPAD;                          // [kParts][3][NPAD] partial sums of the slices
+    double *red = Zx + kParts * 3 * NPAD;               // [kWarps][10]
     double *goal = red + kWarps * 10;                   // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
     unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD]
@@ -90,9 +95,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
         Zx[(part * 3 + 1) * NPAD + node] = z[1];
         Zx[(part * 3 + 2) * NPAD + node] = z[2];
         __syncthreads();
-        z[0] = Zx[0 * NPAD + node] + Zx[3 * NPAD + node];
-        z[1] = Zx[1 * NPAD + node] + Zx[4 * NPAD + node];
-        z[2] = Zx[2 * NPAD + node] + Zx[5 * NPAD + node];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double acc = Zx[q * NPAD + node];
+#pragma unroll
+            for (int pp = 1; pp < kParts; ++pp) acc += Zx[(pp * 3 + q) * NPAD + node];
+            z[q] = acc;
+        }
         __syncthreads();
     };
 
@@ -349,7 +358,7 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     if (!p->dense_target || p->N > NPAD) return 1;
     const int N = p->N;
     const int goal_pad = (p->n_goal + 1) & ~1;
-    size_t smem = ((size_t)N * NPAD + 12 * NPAD + kWarps * 10 + goal_pad) * sizeof(double) + 2 * sizeof(int) +
+    size_t smem = ((size_t)N * NPAD + (6 + 3 * kParts) * NPAD + kWarps * 10 + goal_pad) * sizeof(double) + 2 * sizeof(int) +
                   (size_t)N * NPAD;
     smem = (smem + 15) & ~(size_t)15;
     if (smem > 227 * 1024) return 1;
