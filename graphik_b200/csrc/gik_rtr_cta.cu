@@ -6,11 +6,13 @@
 // term (BASELINE configs[2]); a slot list of ~109 entries per node walked by one lane (k_rtr<32,4>: 436
 // slots per lane and iteration, tables in global memory) leaves the machine idle.  Here
 //
-//   * the targets live as a DENSE matrix T[j][i] in shared memory (N x 128 doubles + a byte of term kind
-//     per pair), loaded once per CTA; the 2 * n_anchor goal-dependent entries are patched per problem;
+//   * per accepted iterate x the pair quantity c2[j][i] = 2 act (d_ij - T_ij) is cached as a DENSE matrix in
+//     shared memory (N x 128 doubles + a byte "hinge active" per pair), rebuilt by the cost/gradient pass of
+//     the proposal from the static targets in global memory (L2) -- the 2 * n_anchor goal-dependent targets
+//     all involve p_n or q_n and live in two per-problem rows Tp, Tq;
 //   * 256 threads: thread t owns node i = t % 128 and one half of the neighbour range j; in the edge pass
 //     every lane of a warp looks at the SAME j, so the neighbour's coordinates are shared-memory
-//     broadcasts and T[j][i] is a conflict-free row read; no index loads at all;
+//     broadcasts and c2[j][i] is a conflict-free row read; no index loads at all;
 //   * the two halves of a node exchange their partial sums through shared memory (fixed order, so both
 //     hold identical bits); inner products are warp butterflies + an 8-entry shared-memory stage, summed
 //     by every thread in the same order -> all scalars are block-uniform and every branch of tCG / RTR is
@@ -58,6 +60,7 @@ struct CtaTables {
     const unsigned char *kind;  // [N][N] GIK_TERM_* or 3 = no term
     const int32_t *goal_i, *goal_j, *goal_slot;
     int n_goal_edges;
+    int gp, gq;                 // node indices of p_n, q_n (-1: no goal-dependent targets)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const CtaTables tb)
@@ -70,21 +73,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
     const bool owner = valid && part == 0;
     const int jchunk = (N + kParts - 1) / kParts;
     const int jlo = part * jchunk, jhi = min(N, jlo + jchunk);
-    double *T = smem;                                   // [N][NPAD]
-    double *P = T + (size_t)N * NPAD;                   // [3][NPAD]
+    double *C2 = smem;                                  // [N][NPAD] 2 act (d - T) at the current iterate
+    double *P = C2 + (size_t)N * NPAD;                  // [3][NPAD]
     double *V = P + 3 * NPAD;                           // [3][NPAD]
     double *Zx = V + 3 * NPAD;                          // [kParts][3][NPAD] partial sums of the slices
     double *red = Zx + kParts * 3 * NPAD;               // [kWarps][10]
-    double *goal = red + kWarps * 10;                   // [n_goal]
+    double *Tp = red + kWarps * 10;                     // [NPAD] targets of the pairs (., p_n) for this problem
+    double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
+    double *goal = Tq + NPAD;                           // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
-    unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD]
+    unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD] static term kind
+    unsigned char *Ak = Kd + (size_t)N * NPAD;                       // [N][NPAD] term active at the current iterate
+    const int gp = tb.gp, gq = tb.gq;
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;
 
     // ---- static tables once per CTA (transposed so that a warp reads a row of consecutive i)
     for (int e = tid; e < N * NPAD; e += kThreads) {
         const int j = e / NPAD, i = e % NPAD;
-        T[e] = i < N ? tb.target[(size_t)i * N + j] : 0.0;
         Kd[e] = i < N ? tb.kind[(size_t)i * N + j] : 3;
     }
     __syncthreads();
@@ -114,7 +120,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                 const unsigned kind = Kd[j * NPAD + node];
                 const double dx = p[0] - P[j], dy = p[1] - P[NPAD + j], dz = p[2] - P[2 * NPAD + j];
                 const double d = dx * dx + dy * dy + dz * dz;
-                double rr = d - T[j * NPAD + node];
+                const double tgt = j == gp ? Tp[node] : (j == gq ? Tq[node] :
+                                   (node == gp ? Tp[j] : (node == gq ? Tq[j] : tb.target[(size_t)j * N + node])));
+                double rr = d - tgt;
                 const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
                                  ((kind == GIK_TERM_UP) & (rr > 0.0));
                 rr = act ? rr : 0.0;
@@ -122,6 +130,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                 gx = fma(rr, dx, gx);
                 gy = fma(rr, dy, gy);
                 gz = fma(rr, dz, gz);
+                C2[j * NPAD + node] = 2.0 * rr;
+                Ak[j * NPAD + node] = act;
             }
         }
         gout[0] = 2.0 * gx; gout[1] = 2.0 * gy; gout[2] = 2.0 * gz;
@@ -135,22 +145,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
         if (valid) {
 #pragma unroll 4
             for (int j = jlo; j < jhi; ++j) {
-                const unsigned kind = Kd[j * NPAD + node];
+                const double c2 = C2[j * NPAD + node];
+                const bool act = Ak[j * NPAD + node] != 0;
                 const double dx = xx[0] - P[j], dy = xx[1] - P[NPAD + j], dz = xx[2] - P[2 * NPAD + j];
                 const double wx = w[0] - V[j], wy = w[1] - V[NPAD + j], wz = w[2] - V[2 * NPAD + j];
-                const double d = dx * dx + dy * dy + dz * dz;
                 const double s = dx * wx + dy * wy + dz * wz;
-                const double rr = d - T[j * NPAD + node];
-                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
-                                 ((kind == GIK_TERM_UP) & (rr > 0.0));
-                const double aa = act ? 2.0 * s : 0.0;
-                const double bb = act ? rr : 0.0;
-                zx = fma(aa, dx, fma(bb, wx, zx));
-                zy = fma(aa, dy, fma(bb, wy, zy));
-                zz = fma(aa, dz, fma(bb, wz, zz));
+                const double aa = act ? 4.0 * s : 0.0;
+                zx = fma(aa, dx, fma(c2, wx, zx));
+                zy = fma(aa, dy, fma(c2, wy, zy));
+                zz = fma(aa, dz, fma(c2, wz, zz));
             }
         }
-        z[0] = 2.0 * zx; z[1] = 2.0 * zy; z[2] = 2.0 * zz;
+        z[0] = zx; z[1] = zy; z[2] = zz;
         combine3(z);
     };
 
@@ -173,11 +179,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
         for (int k = tid; k < a.n_goal; k += kThreads) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
         publish(P, x);
         __syncthreads();
-        for (int e = tid; e < tb.n_goal_edges; e += kThreads) {
-            const int i = tb.goal_i[e], j = tb.goal_j[e];
-            const double t = goal[tb.goal_slot[e]];
-            T[j * NPAD + i] = t;
-            T[i * NPAD + j] = t;
+        if (gp >= 0) {
+            for (int i = tid; i < N; i += kThreads) {
+                Tp[i] = tb.target[(size_t)gp * N + i];
+                Tq[i] = tb.target[(size_t)gq * N + i];
+            }
+            __syncthreads();
+            for (int e = tid; e < tb.n_goal_edges; e += kThreads) {
+                const int i = tb.goal_i[e], j = tb.goal_j[e];
+                const double t = goal[tb.goal_slot[e]];
+                if (j == gp) Tp[i] = t; else if (i == gp) Tp[j] = t;
+                if (j == gq) Tq[i] = t; else if (i == gq) Tq[j] = t;
+            }
         }
         __syncthreads();
 
@@ -318,9 +331,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                     norm_grad = sqrt(gg);
                     gik_sylvester_inverse(v + 4, Mi);
                 } else {
+                    // rejected: bring the exchange buffer and the pair cache back to x
                     __syncthreads();
                     publish(P, x);
                     __syncthreads();
+                    double gtmp[3];
+                    cost_grad(x, gtmp);
                 }
                 if (a.trace && k_outer < a.trace_rows && tid == 0) {
                     double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
@@ -358,8 +374,8 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     if (!p->dense_target || p->N > NPAD) return 1;
     const int N = p->N;
     const int goal_pad = (p->n_goal + 1) & ~1;
-    size_t smem = ((size_t)N * NPAD + (6 + 3 * kParts) * NPAD + kWarps * 10 + goal_pad) * sizeof(double) + 2 * sizeof(int) +
-                  (size_t)N * NPAD;
+    size_t smem = ((size_t)N * NPAD + (8 + 3 * kParts) * NPAD + kWarps * 10 + goal_pad) * sizeof(double) + 2 * sizeof(int) +
+                  2 * (size_t)N * NPAD;
     smem = (smem + 15) & ~(size_t)15;
     if (smem > 227 * 1024) return 1;
     GIK_CUDA(cudaFuncSetAttribute(k_rtr_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,6 +391,8 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     tb.goal_j = p->dense_goal_j;
     tb.goal_slot = p->dense_goal_slot;
     tb.n_goal_edges = p->n_dense_goal;
+    tb.gp = p->n_dense_goal > 0 ? p->goal_p : -1;
+    tb.gq = p->n_dense_goal > 0 ? p->goal_q : -1;
     GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
     k_rtr_cta<<<blocks, kThreads, smem, st>>>(a, tb);
     return gik_check_cuda(cudaGetLastError(), "k_rtr_cta launch");
