@@ -44,9 +44,20 @@ class RiemannianSolver:
     # -- engine bound to the graph (pose-goal pipeline) -------------------------
     @property
     def engine(self) -> BatchIK:
-        if self._engine is None or self._engine.plan.N != self.graph.number_of_nodes():
-            self._engine = BatchIK(self.graph, self.params)
-            self.N = self.graph.number_of_nodes()
+        """Device plan + buffers for this graph.  The reference builds a RiemannianSolver per call
+        (riemannian_solver.py:222); to keep that usage cheap the engine is cached on the graph object and
+        rebuilt only when the graph's edge data changed (e.g. an obstacle was added)."""
+        g = self.graph
+        sig = hash((g.number_of_nodes(), g.dist.tobytes(), g.lower.tobytes(), g.upper.tobytes(),
+                    g.below.tobytes(), g.above.tobytes()))
+        cached = getattr(g, "_gik_engine_cache", None)
+        if self._engine is None and cached is not None and cached[0] == sig:
+            self._engine = cached[1]
+        if self._engine is None or getattr(self, "_engine_sig", sig) != sig:
+            self._engine = BatchIK(g, self.params)
+        self._engine_sig = sig
+        g._gik_engine_cache = (sig, self._engine)
+        self.N = g.number_of_nodes()
         return self._engine
 
     # -- reference API -------------------------------------------------------------

@@ -143,3 +143,17 @@ def test_c_abi_error_codes_and_empty_batches():
     # empty batch through the Python engine
     out = eng.solve(np.zeros((0, 4, 4)), check=False)
     assert out["q"].shape == (0, 6) and out["x"].shape == (0, 16, 3)
+
+
+def test_engine_is_cached_on_the_graph_and_invalidated_by_edits():
+    from graphik_b200.solvers.riemannian_solver import RiemannianSolver, solve_with_riemannian
+    robot, graph = load_robot("ur10")
+    g = golden("ur10_goals")
+    solve_with_riemannian(graph, g["T_goal"][0])
+    eng1 = graph._gik_engine_cache[1]
+    solve_with_riemannian(graph, g["T_goal"][1])
+    assert graph._gik_engine_cache[1] is eng1                  # same device plan reused
+    graph.add_spherical_obstacle("o0", np.array([0.5, 0.5, 0.5]), 0.1)
+    q, Y = solve_with_riemannian(graph, g["T_goal"][1])
+    assert graph._gik_engine_cache[1] is not eng1 and Y.shape == (17, 3)
+    assert RiemannianSolver(graph).engine is graph._gik_engine_cache[1]
