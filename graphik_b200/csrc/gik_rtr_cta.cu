@@ -2,21 +2,27 @@
 //
 // Same algorithm and arithmetic conventions as the warp kernels (reference trust_region.py:112-599,
 // costs.py:79-207, fixed_rank_psd_sym.py:91-137).  With spherical obstacles the reference's graph has
-// N = 118 nodes of which 104 are mutually fixed anchors, i.e. 5609 of 6903 node pairs carry an equality
-// term (BASELINE configs[2]); a slot list of ~109 entries per node walked by one lane (k_rtr<32,4>: 436
-// slots per lane and iteration, tables in global memory) leaves the machine idle.  Here
+// N = 118 nodes of which 106 are mutually fixed anchors, i.e. 5609 of 6903 node pairs carry an equality
+// term (BASELINE configs[2]) and a solve needs ~90 k tCG iterations of 13.8 k directed pair evaluations.
+// The inner iteration is FP64-issue bound (15 FP64 instructions per directed pair), so the layout is
+// chosen to keep everything else off the FP64 pipe's back:
 //
 //   * per accepted iterate x the pair quantity c2[j][i] = 2 act (d_ij - T_ij) is cached as a DENSE matrix in
-//     shared memory (N x 128 doubles + a byte "hinge active" per pair), rebuilt by the cost/gradient pass of
-//     the proposal from the static targets in global memory (L2) -- the 2 * n_anchor goal-dependent targets
-//     all involve p_n or q_n and live in two per-problem rows Tp, Tq;
-//   * 256 threads: thread t owns node i = t % 128 and one half of the neighbour range j; in the edge pass
-//     every lane of a warp looks at the SAME j, so the neighbour's coordinates are shared-memory
-//     broadcasts and c2[j][i] is a conflict-free row read; no index loads at all;
-//   * the two halves of a node exchange their partial sums through shared memory (fixed order, so both
-//     hold identical bits); inner products are warp butterflies + an 8-entry shared-memory stage, summed
-//     by every thread in the same order -> all scalars are block-uniform and every branch of tCG / RTR is
-//     taken by the whole CTA.
+//     shared memory (N x 128 doubles), the hinge activity as a bit mask in registers; both are rebuilt by
+//     the cost/gradient pass of the proposal from the static targets in global memory (L2) -- the
+//     2 * n_anchor goal-dependent targets all involve p_n or q_n and live in two per-problem rows Tp, Tq;
+//   * REGISTER TILE: warp w owns the neighbour slice j in [w JS, (w+1) JS), lane l the four nodes
+//     i = l, l+32, l+64, l+96.  Per neighbour j a warp issues 6 shared-memory broadcasts (2 x_j, delta_j)
+//     and 4 conflict-free row reads of c2 for 4 x 32 pairs = 60 FP64 instructions per lane in 12 independent
+//     accumulator chains (the first version of this kernel had one node per thread: 8 loads per 16 FP64
+//     instructions and 7 CTA barriers per iteration, 10 k cycles per iteration against an FP64 bound of 3.3 k);
+//   * coordinates are exchanged DOUBLED (2 x): D' = 2 (x_i - x_j) gives 4 <D,w> D = <D',w> D' and
+//     2 r D = r D' with exact power-of-two scalings, i.e. bit-identical terms with one multiply less;
+//   * the slices' partial node sums go through shared memory and are added in slice order by the node's
+//     owner thread (t < 128 owns node t and its solver state x, g, eta, Heta, r, delta in registers);
+//     inner products are warp butterflies of the owner warps + a 4-entry shared-memory stage read by every
+//     thread in the same order -> all scalars are block-uniform, every branch of tCG / RTR is taken by the
+//     whole CTA, and an inner iteration has 4 CTA barriers.
 //
 // A pair carrying more than one term kind is not representable densely; gik_launch_rtr_cta then returns 1
 // and the caller falls back to k_rtr.
@@ -27,33 +33,14 @@ namespace {
 #ifndef GIK_CTA_THREADS
 #define GIK_CTA_THREADS 256
 #endif
-constexpr int kThreads = GIK_CTA_THREADS;   // 2 (or 4) threads per node, each owning a slice of the neighbour range
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = GIK_CTA_THREADS;
+constexpr int kWarps = kThreads / 32;       // neighbour slices
 constexpr int NPAD = 128;
-constexpr int kParts = kThreads / NPAD;
-
-template <int K>
-__device__ __forceinline__ void block_allreduce(double (&v)[K], double *red, int warp, int lane)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double s = red[k];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) s += red[w * K + k];
-        v[k] = s;
-    }
-    __syncthreads();
-}
+constexpr int kTile = NPAD / 32;            // nodes per lane in the pair passes
+constexpr int kOwnWarps = NPAD / 32;        // warps whose threads own a node
+constexpr int JSMAX = (NPAD + kWarps - 1) / kWarps;
+constexpr int kRedA = 10, kRedB = 4;
+static_assert(kTile * JSMAX <= 64, "activity mask is one 64-bit word per lane");
 
 struct CtaTables {
     const double *target;       // [N][N] squared targets (static part)
@@ -63,27 +50,56 @@ struct CtaTables {
     int gp, gq;                 // node indices of p_n, q_n (-1: no goal-dependent targets)
 };
 
+// butterfly over a warp, lane 0 stores K partial sums
+template <int K>
+__device__ __forceinline__ void warp_sum_store(double (&v)[K], double *dst, bool store)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
+    }
+    if (store) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) dst[k] = v[k];
+    }
+}
+
+// every thread adds the owner warps' partial sums in the same order
+template <int K, int STRIDE>
+__device__ __forceinline__ void block_sum_load(double (&v)[K], const double *src)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = src[k];
+#pragma unroll
+        for (int w = 1; w < kOwnWarps; ++w) s += src[w * STRIDE + k];
+        v[k] = s;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const CtaTables tb)
 {
     extern __shared__ double smem[];
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int node = tid % NPAD, part = tid / NPAD;
-    const bool valid = node < N;
-    const bool owner = valid && part == 0;
-    const int jchunk = (N + kParts - 1) / kParts;
-    const int jlo = part * jchunk, jhi = min(N, jlo + jchunk);
-    double *C2 = smem;                                  // [N][NPAD] 2 act (d - T) at the current iterate
-    double *P = C2 + (size_t)N * NPAD;                  // [3][NPAD]
-    double *V = P + 3 * NPAD;                           // [3][NPAD]
-    double *Zx = V + 3 * NPAD;                          // [kParts][3][NPAD] partial sums of the slices
-    double *red = Zx + kParts * 3 * NPAD;               // [kWarps][10]
-    double *Tp = red + kWarps * 10;                     // [NPAD] targets of the pairs (., p_n) for this problem
+    const bool first_of_own_warp = lane == 0 && warp < kOwnWarps;   // stores its warp's partial inner products
+    const bool owner = tid < N;                     // thread tid owns node tid
+    const int JS = (N + kWarps - 1) / kWarps;
+    const int jlo = warp * JS;
+    const int jn = max(0, min(N, jlo + JS) - jlo);  // neighbours in this warp's slice
+    double *C2 = smem;                                  // [N][NPAD] 2 act (d - T) at the cached point
+    double *P2 = C2 + (size_t)N * NPAD;                 // [3][NPAD] 2 * coordinates of the cached point
+    double *V = P2 + 3 * NPAD;                          // [3][NPAD] direction delta
+    double *Zp = V + 3 * NPAD;                          // [kWarps][3][NPAD] partial node sums of the slices
+    double *redA = Zp + kWarps * 3 * NPAD;              // [kOwnWarps][kRedA]
+    double *redB = redA + kOwnWarps * kRedA;            // [kOwnWarps][kRedB]
+    double *redF = redB + kOwnWarps * kRedB;            // [kWarps] cost shares of the slices
+    double *Tp = redF + kWarps;                         // [NPAD] targets of the pairs (., p_n) for this problem
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
     double *goal = Tq + NPAD;                           // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
-    unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD] static term kind
-    unsigned char *Ak = Kd + (size_t)N * NPAD;                       // [N][NPAD] term active at the current iterate
+    unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD] static term kind, [j][i]
     const int gp = tb.gp, gq = tb.gq;
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;
@@ -93,75 +109,112 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
         const int j = e / NPAD, i = e % NPAD;
         Kd[e] = i < N ? tb.kind[(size_t)i * N + j] : 3;
     }
+    for (int e = tid; e < 3 * NPAD; e += kThreads) { P2[e] = 0.0; V[e] = 0.0; }   // padding nodes stay at 0
     __syncthreads();
 
-    // combine the partial node sums of the two halves in a fixed order
-    auto combine3 = [&](double (&z)[3]) {
-        Zx[(part * 3 + 0) * NPAD + node] = z[0];
-        Zx[(part * 3 + 1) * NPAD + node] = z[1];
-        Zx[(part * 3 + 2) * NPAD + node] = z[2];
-        __syncthreads();
+    double xt[kTile][3];        // 2 * coordinates of this lane's tile nodes at the cached point
+    unsigned long long amask = 0ull;   // bit m * JSMAX + jj: term (tile node m, neighbour jlo + jj) active there
+
+    auto load_tile = [&](const double *buf, double (&t)[kTile][3]) {
+#pragma unroll
+        for (int m = 0; m < kTile; ++m) {
+            t[m][0] = buf[lane + 32 * m];
+            t[m][1] = buf[NPAD + lane + 32 * m];
+            t[m][2] = buf[2 * NPAD + lane + 32 * m];
+        }
+    };
+    auto store_partials = [&](const double (&z)[kTile][3]) {
+#pragma unroll
+        for (int m = 0; m < kTile; ++m) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + lane + 32 * m] = z[m][q];
+        }
+    };
+    // owner: sum of the slices' partial sums of its node, in slice order
+    auto gather = [&](double (&z)[3]) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            double acc = Zx[q * NPAD + node];
+            double acc = Zp[q * NPAD + tid];
 #pragma unroll
-            for (int pp = 1; pp < kParts; ++pp) acc += Zx[(pp * 3 + q) * NPAD + node];
+            for (int w = 1; w < kWarps; ++w) acc += Zp[(w * 3 + q) * NPAD + tid];
             z[q] = acc;
         }
-        __syncthreads();
+    };
+    auto publish = [&](double *buf, const double (&v)[3], double scale) {
+        if (owner) { buf[tid] = scale * v[0]; buf[NPAD + tid] = scale * v[1]; buf[2 * NPAD + tid] = scale * v[2]; }
     };
 
-    // costs.py:125-169 at point p (published in P): this thread's cost share, full half-gradient of the node
-    auto cost_grad = [&](const double (&p)[3], double (&gout)[3]) -> double {
-        double fpart = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
-        if (valid) {
-#pragma unroll 4
-            for (int j = jlo; j < jhi; ++j) {
-                const unsigned kind = Kd[j * NPAD + node];
-                const double dx = p[0] - P[j], dy = p[1] - P[NPAD + j], dz = p[2] - P[2 * NPAD + j];
-                const double d = dx * dx + dy * dy + dz * dz;
-                const double tgt = j == gp ? Tp[node] : (j == gq ? Tq[node] :
-                                   (node == gp ? Tp[j] : (node == gq ? Tq[j] : tb.target[(size_t)j * N + node])));
-                double rr = d - tgt;
+    // costs.py:125-169 at the point published (doubled) in P2: rebuilds xt, C2 and the activity mask, leaves the
+    // slices' partial half-gradients in Zp and their cost shares in redF.  Caller synchronises before and after.
+    auto pair_pass_cost = [&]() {
+        load_tile(P2, xt);
+        double gpart[kTile][3];
+        double fpart = 0.0;
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int m = 0; m < kTile; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; }
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = jlo + jj;
+            const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+#pragma unroll
+            for (int m = 0; m < kTile; ++m) {
+                const int i = lane + 32 * m;
+                const unsigned kind = Kd[j * NPAD + i];
+                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;   // 2 (x_i - x_j)
+                const double d4 = dx * dx + dy * dy + dz * dz;                               // 4 d_ij
+                const int ic = min(i, N - 1);
+                const double tgt = j == gp ? Tp[ic] : (j == gq ? Tq[ic] :
+                                   (i == gp ? Tp[j] : (i == gq ? Tq[j] : tb.target[(size_t)j * N + ic])));
+                double rr = fma(0.25, d4, -tgt);                                             // d_ij - T_ij
                 const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
                                  ((kind == GIK_TERM_UP) & (rr > 0.0));
                 rr = act ? rr : 0.0;
                 fpart = fma(rr, rr, fpart);
-                gx = fma(rr, dx, gx);
-                gy = fma(rr, dy, gy);
-                gz = fma(rr, dz, gz);
-                C2[j * NPAD + node] = 2.0 * rr;
-                Ak[j * NPAD + node] = act;
+                gpart[m][0] = fma(rr, dx, gpart[m][0]);      // 2 r (x_i - x_j)
+                gpart[m][1] = fma(rr, dy, gpart[m][1]);
+                gpart[m][2] = fma(rr, dz, gpart[m][2]);
+                C2[j * NPAD + i] = 2.0 * rr;
+                mask |= (unsigned long long)act << (m * JSMAX + jj);
             }
         }
-        gout[0] = 2.0 * gx; gout[1] = 2.0 * gy; gout[2] = 2.0 * gz;
-        combine3(gout);
-        return 0.5 * fpart;
+        amask = mask;
+        store_partials(gpart);
+        double f1[1] = {0.5 * fpart};   // every undirected term is seen from both ends
+        warp_sum_store<1>(f1, redF + warp, lane == 0);
     };
 
-    // costs.py:171-207 at x (in P) along w (in V)
-    auto hess = [&](const double (&xx)[3], const double (&w)[3], double (&z)[3]) {
-        double zx = 0.0, zy = 0.0, zz = 0.0;
-        if (valid) {
-#pragma unroll 4
-            for (int j = jlo; j < jhi; ++j) {
-                const double c2 = C2[j * NPAD + node];
-                const bool act = Ak[j * NPAD + node] != 0;
-                const double dx = xx[0] - P[j], dy = xx[1] - P[NPAD + j], dz = xx[2] - P[2 * NPAD + j];
-                const double wx = w[0] - V[j], wy = w[1] - V[NPAD + j], wz = w[2] - V[2 * NPAD + j];
-                const double s = dx * wx + dy * wy + dz * wz;
-                const double aa = act ? 4.0 * s : 0.0;
-                zx = fma(aa, dx, fma(c2, wx, zx));
-                zy = fma(aa, dy, fma(c2, wy, zy));
-                zz = fma(aa, dz, fma(c2, wz, zz));
+    // costs.py:171-207 at the cached point along the direction published in V: partial sums into Zp
+    auto pair_pass_hess = [&]() {
+        double wt[kTile][3], z[kTile][3];
+        load_tile(V, wt);
+#pragma unroll
+        for (int m = 0; m < kTile; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
+#pragma unroll 3
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = jlo + jj;
+            const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+            const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
+            const unsigned long long mj = amask >> jj;
+#pragma unroll
+            for (int m = 0; m < kTile; ++m) {
+                const double c2 = C2[j * NPAD + lane + 32 * m];
+                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
+                double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
+                s = ((mj >> (m * JSMAX)) & 1ull) ? s : 0.0;
+                z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
+                z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
+                z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
             }
         }
-        z[0] = zx; z[1] = zy; z[2] = zz;
-        combine3(z);
+        store_partials(z);
     };
 
-    auto publish = [&](double *buf, const double (&v)[3]) {
-        if (part == 0) { buf[node] = v[0]; buf[NPAD + node] = v[1]; buf[2 * NPAD + node] = v[2]; }
+    auto total_cost = [&]() -> double {
+        double f = redF[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) f += redF[w];
+        return f;
     };
 
     for (;;) {
@@ -171,20 +224,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
         __syncthreads();
         if (b >= a.B) break;
 
-        double x[3] = {0.0, 0.0, 0.0}, g[3], eta[3], Heta[3], r[3], dl[3], Hd[3];
-        if (valid) {
-            const double *src = a.Y_init + ((size_t)b * N + node) * 3;
+        double x[3] = {0.0, 0.0, 0.0}, g[3] = {0.0, 0.0, 0.0}, eta[3], Heta[3], r[3], dl[3], Hd[3] = {0.0, 0.0, 0.0};
+        if (owner) {
+            const double *src = a.Y_init + ((size_t)b * N + tid) * 3;
             x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
         }
         for (int k = tid; k < a.n_goal; k += kThreads) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
-        publish(P, x);
-        __syncthreads();
+        publish(P2, x, 2.0);
         if (gp >= 0) {
             for (int i = tid; i < N; i += kThreads) {
                 Tp[i] = tb.target[(size_t)gp * N + i];
                 Tq[i] = tb.target[(size_t)gq * N + i];
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        if (gp >= 0) {
             for (int e = tid; e < tb.n_goal_edges; e += kThreads) {
                 const int i = tb.goal_i[e], j = tb.goal_j[e];
                 const double t = goal[tb.goal_slot[e]];
@@ -196,18 +250,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 
         double fx, gg, Mi[6];
         {
-            double v[8];
-            v[0] = cost_grad(x, g);
-            const double w8 = owner ? 1.0 : 0.0;   // node quantities are counted once (by the first half)
-            v[1] = w8 * (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
-            v[2] = w8 * x[0] * x[0]; v[3] = w8 * x[0] * x[1]; v[4] = w8 * x[0] * x[2];
-            v[5] = w8 * x[1] * x[1]; v[6] = w8 * x[1] * x[2]; v[7] = w8 * x[2] * x[2];
-            block_allreduce<8>(v, red, warp, lane);
-            fx = v[0];
-            gg = v[1];
-            gik_sylvester_inverse(v + 2, Mi);
+            pair_pass_cost();
+            __syncthreads();
+            if (owner) gather(g);
+            // threads without a node carry zeros in all node state, so every warp can run the butterflies
+            double v[7] = {g[0] * g[0] + g[1] * g[1] + g[2] * g[2],
+                           x[0] * x[0], x[0] * x[1], x[0] * x[2], x[1] * x[1], x[1] * x[2], x[2] * x[2]};
+            warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
+            __syncthreads();
+            block_sum_load<7, kRedA>(v, redA);
+            fx = total_cost();
+            gg = v[0];
+            gik_sylvester_inverse(v + 1, Mi);
         }
-        const double w1 = owner ? 1.0 : 0.0;
         double norm_grad = sqrt(gg);
         double Delta = o.Delta0;
         int k_outer = 0, inner_total = 0, status = GIK_STATUS_MAXITER;
@@ -227,19 +282,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                 const double Delta2 = Delta * Delta;
                 int stop = MAX_INNER_ITER;
                 int j = 0;
+                __syncthreads();          // every reader of V / redA / redB of the previous phase is done
+                publish(V, dl, 1.0);
                 for (j = 0; j < o.maxinner; ++j) {
-                    publish(V, dl);
-                    __syncthreads();
-                    hess(x, dl, Hd);   // raw Z; projected below
+                    __syncthreads();                                   // (1) delta published
+                    pair_pass_hess();
+                    __syncthreads();                                   // (2) partial sums complete
+                    if (owner) gather(Hd);                             // raw Z; projected below
+                    else { Hd[0] = 0.0; Hd[1] = 0.0; Hd[2] = 0.0; }
                     double v[7];
-                    v[0] = w1 * (dl[0] * Hd[0] + dl[1] * Hd[1] + dl[2] * Hd[2]);
-                    v[1] = w1 * (Hd[1] * x[2] - Hd[2] * x[1]);      // c = sum Z_i x Y_i
-                    v[2] = w1 * (Hd[2] * x[0] - Hd[0] * x[2]);
-                    v[3] = w1 * (Hd[0] * x[1] - Hd[1] * x[0]);
-                    v[4] = w1 * (dl[1] * x[2] - dl[2] * x[1]);      // u = sum delta_i x Y_i
-                    v[5] = w1 * (dl[2] * x[0] - dl[0] * x[2]);
-                    v[6] = w1 * (dl[0] * x[1] - dl[1] * x[0]);
-                    block_allreduce<7>(v, red, warp, lane);
+                    v[0] = dl[0] * Hd[0] + dl[1] * Hd[1] + dl[2] * Hd[2];
+                    v[1] = Hd[1] * x[2] - Hd[2] * x[1];                // c = sum Z_i x Y_i
+                    v[2] = Hd[2] * x[0] - Hd[0] * x[2];
+                    v[3] = Hd[0] * x[1] - Hd[1] * x[0];
+                    v[4] = dl[1] * x[2] - dl[2] * x[1];                // u = sum delta_i x Y_i
+                    v[5] = dl[2] * x[0] - dl[0] * x[2];
+                    v[6] = dl[0] * x[1] - dl[1] * x[0];
+                    warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
+                    __syncthreads();                                   // (3)
+                    block_sum_load<7, kRedA>(v, redA);
                     double om[3];
                     gik_sym_mul(Mi, v + 1, om);
                     Hd[0] -= x[1] * om[2] - x[2] * om[1];
@@ -260,19 +321,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                         break;
                     }
                     e_Pe = e_Pe_new;
-                    double ne[3], nh[3], nr[3], sdot[3] = {0.0, 0.0, 0.0};
+                    double ne[3], nh[3], nr[3];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         ne[q] = fma(alpha, dl[q], eta[q]);
                         nh[q] = fma(alpha, Hd[q], Heta[q]);
                         nr[q] = fma(alpha, Hd[q], r[q]);
-                        sdot[0] = fma(ne[q], g[q], sdot[0]);
-                        sdot[1] = fma(ne[q], nh[q], sdot[1]);
-                        sdot[2] = fma(nr[q], nr[q], sdot[2]);
                     }
-                    sdot[0] *= w1; sdot[1] *= w1; sdot[2] *= w1;
-                    block_allreduce<3>(sdot, red, warp, lane);
-                    const double new_model_value = sdot[0] + 0.5 * sdot[1];
+                    {
+                        double sdot[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            sdot[0] = fma(ne[q], g[q], sdot[0]);
+                            sdot[1] = fma(ne[q], nh[q], sdot[1]);
+                            sdot[2] = fma(nr[q], nr[q], sdot[2]);
+                        }
+                        warp_sum_store<3>(sdot, redB + warp * kRedB, first_of_own_warp);
+                    }
+                    __syncthreads();                                   // (4)
+                    double sd[3];
+                    block_sum_load<3, kRedB>(sd, redB);
+                    const double new_model_value = sd[0] + 0.5 * sd[1];
                     if (new_model_value >= model_value) {
                         stop = MODEL_INCREASED;
                         break;
@@ -280,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { eta[q] = ne[q]; Heta[q] = nh[q]; r[q] = nr[q]; }
                     model_value = new_model_value;
-                    r_r = sdot[2];
+                    r_r = sd[2];
                     if (j >= o.mininner && r_r <= r_target2) {
                         stop = o.kappa < pw ? REACHED_TARGET_LINEAR : REACHED_TARGET_SUPERLINEAR;
                         break;
@@ -291,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
                     for (int q = 0; q < 3; ++q) dl[q] = fma(beta, dl[q], -r[q]);
                     e_Pd = beta * (e_Pd + alpha * d_Pd);
                     d_Pd = z_r + beta * beta * d_Pd;
+                    publish(V, dl, 1.0);        // the pair pass read V before barrier (2)
                 }
                 const int numit = j < o.maxinner ? j : o.maxinner - 1;
 
@@ -298,19 +368,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 #pragma unroll
                 for (int q = 0; q < 3; ++q) dl[q] = x[q] + eta[q];
                 __syncthreads();
-                publish(P, dl);
+                publish(P2, dl, 2.0);
                 __syncthreads();
-                double v[10];
-                v[0] = cost_grad(dl, Hd);
-                v[1] = w1 * (g[0] * eta[0] + g[1] * eta[1] + g[2] * eta[2]);
-                v[2] = w1 * (eta[0] * Heta[0] + eta[1] * Heta[1] + eta[2] * Heta[2]);
-                v[3] = w1 * (Hd[0] * Hd[0] + Hd[1] * Hd[1] + Hd[2] * Hd[2]);
-                v[4] = w1 * dl[0] * dl[0]; v[5] = w1 * dl[0] * dl[1]; v[6] = w1 * dl[0] * dl[2];
-                v[7] = w1 * dl[1] * dl[1]; v[8] = w1 * dl[1] * dl[2]; v[9] = w1 * dl[2] * dl[2];
-                block_allreduce<10>(v, red, warp, lane);
-                const double fx_prop = v[0];
+                pair_pass_cost();
+                __syncthreads();
+                if (owner) gather(Hd);
+                else { Hd[0] = 0.0; Hd[1] = 0.0; Hd[2] = 0.0; }
+                double v[9];
+                v[0] = g[0] * eta[0] + g[1] * eta[1] + g[2] * eta[2];
+                v[1] = eta[0] * Heta[0] + eta[1] * Heta[1] + eta[2] * Heta[2];
+                v[2] = Hd[0] * Hd[0] + Hd[1] * Hd[1] + Hd[2] * Hd[2];
+                v[3] = dl[0] * dl[0]; v[4] = dl[0] * dl[1]; v[5] = dl[0] * dl[2];
+                v[6] = dl[1] * dl[1]; v[7] = dl[1] * dl[2]; v[8] = dl[2] * dl[2];
+                warp_sum_store<9>(v, redA + warp * kRedA, first_of_own_warp);
+                __syncthreads();
+                block_sum_load<9, kRedA>(v, redA);
+                const double fx_prop = total_cost();
                 double rhonum = fx - fx_prop;
-                double rhoden = -v[1] - 0.5 * v[2];
+                double rhoden = -v[0] - 0.5 * v[1];
                 const double rho_reg = fmax(1.0, fabs(fx)) * eps * o.rho_regularization;
                 rhonum += rho_reg;
                 rhoden += rho_reg;
@@ -327,16 +402,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { x[q] = dl[q]; g[q] = Hd[q]; }
                     fx = fx_prop;
-                    gg = v[3];
+                    gg = v[2];
                     norm_grad = sqrt(gg);
-                    gik_sylvester_inverse(v + 4, Mi);
+                    gik_sylvester_inverse(v + 3, Mi);
                 } else {
-                    // rejected: bring the exchange buffer and the pair cache back to x
+                    // rejected: bring the exchange buffer, the tile and the pair cache back to x
                     __syncthreads();
-                    publish(P, x);
+                    publish(P2, x, 2.0);
                     __syncthreads();
-                    double gtmp[3];
-                    cost_grad(x, gtmp);
+                    pair_pass_cost();
                 }
                 if (a.trace && k_outer < a.trace_rows && tid == 0) {
                     double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
@@ -353,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
             }
         }
         if (owner) {
-            double *dst = a.Y_out + ((size_t)b * N + node) * 3;
+            double *dst = a.Y_out + ((size_t)b * N + tid) * 3;
             dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
         }
         if (tid == 0) {
@@ -367,16 +441,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
     }
 }
 
+size_t cta_smem_bytes(int N, int n_goal)
+{
+    const int goal_pad = (n_goal + 1) & ~1;
+    size_t smem = ((size_t)N * NPAD + (6 + 3 * kWarps + 2) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
+                      sizeof(double) + 2 * sizeof(int) + (size_t)N * NPAD;
+    return (smem + 15) & ~(size_t)15;
+}
+
 }  // namespace
 
 int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
     if (!p->dense_target || p->N > NPAD) return 1;
     const int N = p->N;
-    const int goal_pad = (p->n_goal + 1) & ~1;
-    size_t smem = ((size_t)N * NPAD + (8 + 3 * kParts) * NPAD + kWarps * 10 + goal_pad) * sizeof(double) + 2 * sizeof(int) +
-                  2 * (size_t)N * NPAD;
-    smem = (smem + 15) & ~(size_t)15;
+    const size_t smem = cta_smem_bytes(N, p->n_goal);
     if (smem > 227 * 1024) return 1;
     GIK_CUDA(cudaFuncSetAttribute(k_rtr_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

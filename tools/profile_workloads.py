@@ -5,7 +5,8 @@ and FP64 rate (38 flop per term + 60N + 60 per inner iteration).
 
     python tools/profile_workloads.py ur10:4096:latency ur10:65536:throughput chain20:8192 kuka_table:296
 
-Each spec is robot:batch[:kernel[:repeats]].  One JSON line per spec (not a bench value: no e2e, one launch).
+Each spec is robot:batch[:kernel[:repeats[:maxiter]]]; with a small maxiter every problem does about the
+same work, so solve time / max inner iterations is the latency of one inner iteration of one problem.  One JSON line per spec (not a bench value: no e2e, one launch).
 """
 import json
 import os
@@ -30,18 +31,25 @@ def main():
         parts = spec.split(":")
         robot_name, B = parts[0], int(parts[1])
         kernel = parts[2] if len(parts) > 2 and parts[2] else "auto"
-        reps = int(parts[3]) if len(parts) > 3 else 1
+        reps = int(parts[3]) if len(parts) > 3 and parts[3] else 1
+        maxiter = int(parts[4]) if len(parts) > 4 else None
         robot, graph = load_workload(robot_name)
-        eng = BatchIK(graph, params={"kernel": kernel}, device=dev)
+        params = {"kernel": kernel}
+        if maxiter:
+            params["maxiter"] = maxiter
+        eng = BatchIK(graph, params=params, device=dev)
         N = graph.number_of_nodes()
         _, T = goals_for(robot, B, seed=1000)
         T = torch.as_tensor(T, device=dev)
         g2 = eng.goal_distances(T)
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        Y0 = eng.initialization(g2[: min(B, 64)])                   # warm (module load)
+        torch.cuda.synchronize()
         e0.record()
         Y0 = eng.initialization(g2)
         e1.record()
         torch.cuda.synchronize()
+        init_ms = e0.elapsed_time(e1)
         eng.solve_points(g2[: min(B, 64)], Y0[: min(B, 64)])       # warm (module load, smem attribute)
         torch.cuda.synchronize()
         ms = []
@@ -60,13 +68,14 @@ def main():
         flops = float(inn.sum()) * (38.0 * n_terms + 60.0 * N + 60.0)
         line = {
             "robot": robot_name, "B": B, "kernel": kernel, "N": N, "terms": n_terms,
-            "init_ms": e0.elapsed_time(e1), "solve_ms": [round(m, 3) for m in ms],
+            "init_ms": init_ms, "solve_ms": [round(m, 3) for m in ms],
             "solves_per_s": B / t,
             "mean_outer": float(it.mean()), "mean_inner": float(inn.mean()), "max_inner": float(inn.max()),
             "converged_frac": float((out["status"] == 0).double().mean()),
             "median_f": float(f.median()),
             "inner_iters_per_s": float(inn.sum()) / t,
             "sm_ns_per_inner_iter": t * sms / float(inn.sum()) * 1e9,
+            "maxiter": maxiter, "us_per_inner_iter_of_slowest_problem": t / float(inn.max()) * 1e6,
             "stream_GBs": alg_bytes / t / 1e9, "stream_frac": alg_bytes / t / 1e9 / peak,
             "fp64_TFLOPs": flops / t / 1e12,
         }
