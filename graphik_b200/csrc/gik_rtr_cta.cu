@@ -1,28 +1,35 @@
-// gik_rtr_cta.cu -- trust-region solve for LARGE, DENSE graphs (32 < N <= 128): one CTA per problem.
+// gik_rtr_cta.cu -- trust-region solve for LARGE, DENSE graphs (32 < N <= 128): one CTA per problem,
+// two CTAs per SM.
 //
 // Same algorithm and arithmetic conventions as the warp kernels (reference trust_region.py:112-599,
 // costs.py:79-207, fixed_rank_psd_sym.py:91-137).  With spherical obstacles the reference's graph has
 // N = 118 nodes of which 106 are mutually fixed anchors, i.e. 5609 of 6903 node pairs carry an equality
-// term (BASELINE configs[2]) and a solve needs ~90 k tCG iterations of 13.8 k directed pair evaluations.
-// The inner iteration is FP64-issue bound (15 FP64 instructions per directed pair), so the layout is
-// chosen to keep everything else off the FP64 pipe's back:
+// term (BASELINE configs[2]) and a solve needs ~100 k tCG iterations of 13.8 k directed pair evaluations.
+// The pair pass of an inner iteration is FP64-issue bound (15 FP64 instructions per directed pair); the
+// rest of the iteration (two CTA-wide reductions, the projection, alpha / beta, ~300 dependent
+// instructions) is a latency chain during which the FP64 pipe idles.  Layout:
 //
-//   * per accepted iterate x the pair quantity c2[j][i] = 2 act (d_ij - T_ij) is cached as a DENSE matrix in
-//     shared memory (N x 128 doubles), the hinge activity as a bit mask in registers; both are rebuilt by
-//     the cost/gradient pass of the proposal from the static targets in global memory (L2) -- the
-//     2 * n_anchor goal-dependent targets all involve p_n or q_n and live in two per-problem rows Tp, Tq;
+//   * per accepted iterate x the pair quantity c2_ij = 2 act (d_ij - T_ij) is cached in shared memory, the
+//     hinge activity as bit masks in registers; both are rebuilt by the cost/gradient pass of the
+//     proposal from the static targets in global memory (L2) -- the 2 * n_anchor goal-dependent targets
+//     all involve p_n or q_n and live in two per-problem rows Tp, Tq;
+//   * c2 is symmetric and stored PACKED: 32 x 32 blocks (a <= b) with row stride 33, element (p in a, q in b)
+//     at [q][p].  A warp reading "fixed j, lanes over i" hits a row of the block when block(i) <= block(j)
+//     and a column otherwise; the odd stride makes both conflict-free.  74 KB instead of 121 KB for
+//     N = 118, so that TWO CTAs (problems) fit on an SM and one problem's latency chain overlaps the
+//     other's pair pass (ncu, one CTA of 256 threads per SM: FP64 pipe 51 % active, 40 % of the time in the
+//     latency chain);
 //   * REGISTER TILE: warp w owns the neighbour slice j in [w JS, (w+1) JS), lane l the four nodes
 //     i = l, l+32, l+64, l+96.  Per neighbour j a warp issues 6 shared-memory broadcasts (2 x_j, delta_j)
-//     and 4 conflict-free row reads of c2 for 4 x 32 pairs = 60 FP64 instructions per lane in 12 independent
-//     accumulator chains (the first version of this kernel had one node per thread: 8 loads per 16 FP64
-//     instructions and 7 CTA barriers per iteration, 10 k cycles per iteration against an FP64 bound of 3.3 k);
+//     and 4 reads of c2 for 4 x 32 pairs = 60 FP64 instructions per lane in 12 independent accumulator
+//     chains;
 //   * coordinates are exchanged DOUBLED (2 x): D' = 2 (x_i - x_j) gives 4 <D,w> D = <D',w> D' and
 //     2 r D = r D' with exact power-of-two scalings, i.e. bit-identical terms with one multiply less;
 //   * the slices' partial node sums go through shared memory and are added in slice order by the node's
-//     owner thread (t < 128 owns node t and its solver state x, g, eta, Heta, r, delta in registers);
-//     inner products are warp butterflies of the owner warps + a 4-entry shared-memory stage read by every
-//     thread in the same order -> all scalars are block-uniform, every branch of tCG / RTR is taken by the
-//     whole CTA, and an inner iteration has 4 CTA barriers.
+//     owner thread (thread t owns node t and its solver state x, g, eta, Heta, r, delta in registers);
+//     inner products are warp butterflies + a 4-entry shared-memory stage read by every thread in the
+//     same order -> all scalars are block-uniform, every branch of tCG / RTR is taken by the whole CTA,
+//     and an inner iteration has 4 CTA barriers.
 //
 // A pair carrying more than one term kind is not representable densely; gik_launch_rtr_cta then returns 1
 // and the caller falls back to k_rtr.
@@ -30,17 +37,25 @@
 
 namespace {
 
-#ifndef GIK_CTA_THREADS
-#define GIK_CTA_THREADS 256
-#endif
-constexpr int kThreads = GIK_CTA_THREADS;
-constexpr int kWarps = kThreads / 32;       // neighbour slices
 constexpr int NPAD = 128;
-constexpr int kTile = NPAD / 32;            // nodes per lane in the pair passes
-constexpr int kOwnWarps = NPAD / 32;        // warps whose threads own a node
-constexpr int JSMAX = (NPAD + kWarps - 1) / kWarps;
+constexpr int kThreads = NPAD;              // thread t owns node t
+constexpr int kWarps = kThreads / 32;       // neighbour slices
+constexpr int kOwnWarps = kWarps;
+constexpr int kStride = 33;                 // row stride of a packed 32 x 32 block of c2
 constexpr int kRedA = 10, kRedB = 4;
-static_assert(kTile * JSMAX <= 64, "activity mask is one 64-bit word per lane");
+static_assert((NPAD + kWarps - 1) / kWarps <= 32, "one 32-bit activity mask per tile node");
+
+// doubles of the packed symmetric pair cache: column block b holds b + 1 blocks of rows_b rows
+__host__ __device__ inline int c2_rows(int N, int b) { return min(32, N - 32 * b); }
+__host__ __device__ inline int c2_base(int N, int a, int b)   // block (a <= b)
+{
+    return (16 * b * (b + 1) + a * c2_rows(N, b)) * kStride;
+}
+__host__ __device__ inline int c2_doubles(int N)
+{
+    const int nb = (N + 31) / 32;
+    return c2_base(N, nb, nb - 1);   // = end of the last column block
+}
 
 struct CtaTables {
     const double *target;       // [N][N] squared targets (static part)
@@ -78,18 +93,19 @@ __device__ __forceinline__ void block_sum_load(double (&v)[K], const double *src
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const CtaTables tb)
+template <int NB>   // 32-node blocks = nodes per lane in the pair passes
+__global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const CtaTables tb)
 {
     extern __shared__ double smem[];
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool first_of_own_warp = lane == 0 && warp < kOwnWarps;   // stores its warp's partial inner products
+    const bool first_of_own_warp = lane == 0;   // stores its warp's partial inner products
     const bool owner = tid < N;                     // thread tid owns node tid
     const int JS = (N + kWarps - 1) / kWarps;
     const int jlo = warp * JS;
-    const int jn = max(0, min(N, jlo + JS) - jlo);  // neighbours in this warp's slice
-    double *C2 = smem;                                  // [N][NPAD] 2 act (d - T) at the cached point
-    double *P2 = C2 + (size_t)N * NPAD;                 // [3][NPAD] 2 * coordinates of the cached point
+    const int jhi = max(jlo, min(N, jlo + JS));     // this warp's neighbour slice is [jlo, jhi)
+    double *C2 = smem;                                  // packed symmetric 2 act (d - T) at the cached point
+    double *P2 = C2 + c2_doubles(N);                    // [3][NPAD] 2 * coordinates of the cached point
     double *V = P2 + 3 * NPAD;                          // [3][NPAD] direction delta
     double *Zp = V + 3 * NPAD;                          // [kWarps][3][NPAD] partial node sums of the slices
     double *redA = Zp + kWarps * 3 * NPAD;              // [kOwnWarps][kRedA]
@@ -99,33 +115,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
     double *goal = Tq + NPAD;                           // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
-    unsigned char *Kd = reinterpret_cast<unsigned char *>(s_b + 2);  // [N][NPAD] static term kind, [j][i]
     const int gp = tb.gp, gq = tb.gq;
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;
 
-    // ---- static tables once per CTA (transposed so that a warp reads a row of consecutive i)
-    for (int e = tid; e < N * NPAD; e += kThreads) {
-        const int j = e / NPAD, i = e % NPAD;
-        Kd[e] = i < N ? tb.kind[(size_t)i * N + j] : 3;
-    }
+    for (int e = tid; e < c2_doubles(N); e += kThreads) C2[e] = 0.0;
     for (int e = tid; e < 3 * NPAD; e += kThreads) { P2[e] = 0.0; V[e] = 0.0; }   // padding nodes stay at 0
     __syncthreads();
 
-    double xt[kTile][3];        // 2 * coordinates of this lane's tile nodes at the cached point
-    unsigned long long amask = 0ull;   // bit m * JSMAX + jj: term (tile node m, neighbour jlo + jj) active there
-
-    auto load_tile = [&](const double *buf, double (&t)[kTile][3]) {
+    double xt[NB][3];           // 2 * coordinates of this lane's tile nodes at the cached point
+    uint32_t amask[NB];         // bit jj: term (tile node m, neighbour jlo + jj) active there
+    // c2(i = lane + 32 m, j) in the packed cache is a row entry of block (m, jb) when m <= jb and a column
+    // entry of block (jb, m) otherwise; padding lanes of a ragged last block re-read its last row
+    int col_off[NB];
 #pragma unroll
-        for (int m = 0; m < kTile; ++m) {
+    for (int m = 0; m < NB; ++m) {
+        col_off[m] = 16 * m * (m + 1) * kStride + min(lane, c2_rows(N, m) - 1) * kStride;
+        amask[m] = 0u;
+    }
+    // offsets / strides of the NB reads for the neighbours j0, j0 + 1, ... inside block jb
+    auto c2_walk = [&](int jb, int j0, int (&off)[NB], int (&step)[NB]) {
+        const int jl = j0 & 31;
+        const int rows_jb = c2_rows(N, jb);
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            const bool row = m <= jb;
+            off[m] = row ? c2_base(N, 0, jb) + (m * rows_jb + jl) * kStride + lane
+                         : col_off[m] + jb * c2_rows(N, m) * kStride + jl;
+            step[m] = row ? kStride : 1;
+        }
+    };
+
+    auto load_tile = [&](const double *buf, double (&t)[NB][3]) {
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
             t[m][0] = buf[lane + 32 * m];
             t[m][1] = buf[NPAD + lane + 32 * m];
             t[m][2] = buf[2 * NPAD + lane + 32 * m];
         }
     };
-    auto store_partials = [&](const double (&z)[kTile][3]) {
+    auto store_partials = [&](const double (&z)[NB][3]) {
 #pragma unroll
-        for (int m = 0; m < kTile; ++m) {
+        for (int m = 0; m < NB; ++m) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + lane + 32 * m] = z[m][q];
         }
@@ -148,36 +179,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
     // slices' partial half-gradients in Zp and their cost shares in redF.  Caller synchronises before and after.
     auto pair_pass_cost = [&]() {
         load_tile(P2, xt);
-        double gpart[kTile][3];
+        double gpart[NB][3];
         double fpart = 0.0;
-        unsigned long long mask = 0ull;
 #pragma unroll
-        for (int m = 0; m < kTile; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; }
-        for (int jj = 0; jj < jn; ++jj) {
-            const int j = jlo + jj;
-            const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+        for (int m = 0; m < NB; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; amask[m] = 0u; }
+        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
+            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
+            int off[NB], step[NB];
+            c2_walk(jb, j0, off, step);
+            for (int j = j0; j < j1; ++j) {
+                const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+                const uint32_t bit = 1u << (j - jlo);
 #pragma unroll
-            for (int m = 0; m < kTile; ++m) {
-                const int i = lane + 32 * m;
-                const unsigned kind = Kd[j * NPAD + i];
-                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;   // 2 (x_i - x_j)
-                const double d4 = dx * dx + dy * dy + dz * dz;                               // 4 d_ij
-                const int ic = min(i, N - 1);
-                const double tgt = j == gp ? Tp[ic] : (j == gq ? Tq[ic] :
-                                   (i == gp ? Tp[j] : (i == gq ? Tq[j] : tb.target[(size_t)j * N + ic])));
-                double rr = fma(0.25, d4, -tgt);                                             // d_ij - T_ij
-                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
-                                 ((kind == GIK_TERM_UP) & (rr > 0.0));
-                rr = act ? rr : 0.0;
-                fpart = fma(rr, rr, fpart);
-                gpart[m][0] = fma(rr, dx, gpart[m][0]);      // 2 r (x_i - x_j)
-                gpart[m][1] = fma(rr, dy, gpart[m][1]);
-                gpart[m][2] = fma(rr, dz, gpart[m][2]);
-                C2[j * NPAD + i] = 2.0 * rr;
-                mask |= (unsigned long long)act << (m * JSMAX + jj);
+                for (int m = 0; m < NB; ++m) {
+                    const int i = lane + 32 * m;
+                    const unsigned kind = i < N ? tb.kind[(size_t)j * N + i] : 3u;
+                    const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;   // 2 (x_i - x_j)
+                    const double d4 = dx * dx + dy * dy + dz * dz;                               // 4 d_ij
+                    const int ic = min(i, N - 1);
+                    const double tgt = j == gp ? Tp[ic] : (j == gq ? Tq[ic] :
+                                       (i == gp ? Tp[j] : (i == gq ? Tq[j] : tb.target[(size_t)j * N + ic])));
+                    double rr = fma(0.25, d4, -tgt);                                             // d_ij - T_ij
+                    const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
+                                     ((kind == GIK_TERM_UP) & (rr > 0.0));
+                    rr = act ? rr : 0.0;
+                    fpart = fma(rr, rr, fpart);
+                    gpart[m][0] = fma(rr, dx, gpart[m][0]);      // 2 r (x_i - x_j)
+                    gpart[m][1] = fma(rr, dy, gpart[m][1]);
+                    gpart[m][2] = fma(rr, dz, gpart[m][2]);
+                    if (m <= jb) C2[off[m]] = 2.0 * rr;          // the mirrored pair computes the same bits
+                    off[m] += step[m];
+                    amask[m] |= act ? bit : 0u;
+                }
             }
         }
-        amask = mask;
         store_partials(gpart);
         double f1[1] = {0.5 * fpart};   // every undirected term is seen from both ends
         warp_sum_store<1>(f1, redF + warp, lane == 0);
@@ -185,26 +220,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 
     // costs.py:171-207 at the cached point along the direction published in V: partial sums into Zp
     auto pair_pass_hess = [&]() {
-        double wt[kTile][3], z[kTile][3];
+        double wt[NB][3], z[NB][3];
         load_tile(V, wt);
 #pragma unroll
-        for (int m = 0; m < kTile; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
-#pragma unroll 3
-        for (int jj = 0; jj < jn; ++jj) {
-            const int j = jlo + jj;
-            const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
-            const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
-            const unsigned long long mj = amask >> jj;
+        for (int m = 0; m < NB; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
+        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
+            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
+            int off[NB], step[NB];
+            c2_walk(jb, j0, off, step);
+            uint32_t bit = 1u << (j0 - jlo);
+#pragma unroll 2
+            for (int j = j0; j < j1; ++j) {
+                const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+                const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
 #pragma unroll
-            for (int m = 0; m < kTile; ++m) {
-                const double c2 = C2[j * NPAD + lane + 32 * m];
-                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
-                const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
-                double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
-                s = ((mj >> (m * JSMAX)) & 1ull) ? s : 0.0;
-                z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
-                z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
-                z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                for (int m = 0; m < NB; ++m) {
+                    const double c2 = C2[off[m]];
+                    off[m] += step[m];
+                    const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                    const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
+                    double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
+                    s = (amask[m] & bit) ? s : 0.0;
+                    z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
+                    z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
+                    z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                }
+                bit <<= 1;
             }
         }
         store_partials(z);
@@ -444,25 +485,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_rtr_cta(const RtrArgs a, const 
 size_t cta_smem_bytes(int N, int n_goal)
 {
     const int goal_pad = (n_goal + 1) & ~1;
-    size_t smem = ((size_t)N * NPAD + (6 + 3 * kWarps + 2) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
-                      sizeof(double) + 2 * sizeof(int) + (size_t)N * NPAD;
+    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 2) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
+                      sizeof(double) + 2 * sizeof(int);
     return (smem + 15) & ~(size_t)15;
 }
 
 }  // namespace
 
-int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+template <int NB>
+static int launch_cta(const GikPlan *p, RtrArgs &a, const CtaTables &tb, size_t smem, cudaStream_t st)
 {
-    if (!p->dense_target || p->N > NPAD) return 1;
-    const int N = p->N;
-    const size_t smem = cta_smem_bytes(N, p->n_goal);
-    if (smem > 227 * 1024) return 1;
-    GIK_CUDA(cudaFuncSetAttribute(k_rtr_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = k_rtr_cta<NB>;
+    GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtr_cta, kThreads, smem));
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     int blocks = p->sm_count * per_sm;
     if (blocks > a.B) blocks = a.B;
+    GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
+    kern<<<blocks, kThreads, smem, st>>>(a, tb);
+    return gik_check_cuda(cudaGetLastError(), "k_rtr_cta launch");
+}
+
+int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+{
+    if (!p->dense_target || p->N > NPAD || p->N <= 32) return 1;
+    const int N = p->N;
+    const size_t smem = cta_smem_bytes(N, p->n_goal);
+    if (smem > 227 * 1024) return 1;
     CtaTables tb;
     tb.target = p->dense_target;
     tb.kind = p->dense_kind;
@@ -472,7 +522,9 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     tb.n_goal_edges = p->n_dense_goal;
     tb.gp = p->n_dense_goal > 0 ? p->goal_p : -1;
     tb.gq = p->n_dense_goal > 0 ? p->goal_q : -1;
-    GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
-    k_rtr_cta<<<blocks, kThreads, smem, st>>>(a, tb);
-    return gik_check_cuda(cudaGetLastError(), "k_rtr_cta launch");
+    switch ((N + 31) / 32) {
+        case 2: return launch_cta<2>(p, a, tb, smem, st);
+        case 3: return launch_cta<3>(p, a, tb, smem, st);
+        default: return launch_cta<4>(p, a, tb, smem, st);
+    }
 }
