@@ -198,7 +198,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="ur10")
@@ -323,6 +323,10 @@ def main():
     aggregate = alg_bytes_total / (local_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
     workload = "%s_b%d" % (args.robot, B)
+    # secondary bound: algorithmic fp64 flops per tCG iteration = 38 per cost term + 60 N + 60,
+    # against the FP64 FMA peak measured on this pool's B200 with tools/fp64_peak.cu (profiles/r1d_fp64_peak_b200.txt)
+    alg_flops_total = in_sum * (38.0 * eng.plan.n_terms + 60.0 * N + 60.0)
+    fp64_peak_tflops = 34.2
 
     # ------------------------------------------------ end to end through the public API (host buffers)
     from graphik_b200.solvers.riemannian_solver import RiemannianSolver
@@ -399,6 +403,11 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "kernel_ms": rtr_avg_ms, "effective_kernel_ms": local_ms / args.steps,
                          "kernel_share_of_step": float(np.sum(rtr_ms) / np.sum(step_ms)),
+                         "fp64": {"achieved": alg_flops_total / (local_ms * 1e-3) / 1e12, "peak": fp64_peak_tflops,
+                                  "unit": "TFLOP/s", "frac": alg_flops_total / (local_ms * 1e-3) / 1e12 / fp64_peak_tflops,
+                                  "note": "algorithmic flops (38 per term + 60 N + 60 per tCG iteration) / region "
+                                          "time vs the measured FP64 FMA peak; the kernel issues ~2.6x that many "
+                                          "FP64 instructions (terms seen from both end nodes, warp-uniform scalars)"},
                          "note": "algorithmic bytes = sum over problems of 72N*outer + 240N*inner: the state a "
                                  "kernel-per-iteration formulation streams through HBM (SURVEY 8d), from the iteration "
                                  "counts actually executed; the persistent kernel keeps that state in registers (traffic "

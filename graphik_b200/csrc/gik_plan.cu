@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "gik_common.cuh"
@@ -181,6 +182,49 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         }
     }
 
+    // k_rtr_fast2 (32 < N <= 64): nodes ordered by degree; the 32 highest-degree nodes are the lanes' first
+    // nodes, the others the second node of lanes 0 .. N-33.  (S0, S1) = smallest compiled slot counts that fit.
+    std::vector<uint32_t> f2info;
+    std::vector<double> f2target;
+    std::vector<int32_t> f2node;
+    p->fast2_S0 = p->fast2_S1 = 0;
+    if (N > 32 && N <= 64) {
+        std::vector<int> order(N);
+        for (int i = 0; i < N; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return deg[x] > deg[y]; });
+        int need0 = 0, need1 = 0;
+        for (int k = 0; k < N; ++k) {
+            int &need = k < 32 ? need0 : need1;
+            need = deg[order[k]] > need ? deg[order[k]] : need;
+        }
+        static const int combos[][2] = {{6, 5}, {8, 5}, {8, 8}, {12, 8}, {12, 12}};
+        for (const auto &c : combos)
+            if (c[0] >= need0 && c[1] >= need1) { p->fast2_S0 = c[0]; p->fast2_S1 = c[1]; break; }
+        if (p->fast2_S0) {
+            const int S0 = p->fast2_S0, ST = S0 + p->fast2_S1;
+            f2info.assign((size_t)ST * 32, 0u);
+            f2target.assign((size_t)ST * 32, 0.0);
+            f2node.assign(64, -1);
+            for (int l = 0; l < 32; ++l) {
+                for (int m = 0; m < 2; ++m) {
+                    const int k0 = m * 32 + l;
+                    const int node = k0 < N ? order[k0] : -1;
+                    f2node[m * 32 + l] = node;
+                    const int rows = m == 0 ? S0 : p->fast2_S1;
+                    for (int s = 0; s < rows; ++s) {
+                        const size_t at = (size_t)(m * S0 + s) * 32 + l;
+                        if (node >= 0 && s < deg[node]) {
+                            f2info[at] = info[(size_t)s * N + node];
+                            f2target[at] = target[(size_t)s * N + node];
+                        } else {
+                            f2info[at] = (uint32_t)(node >= 0 ? node : 63) | (3u << 16);   // inert: self, no term
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     std::vector<uint32_t> dinfo;
     std::vector<double> dtarget;
     if (N <= 16 && maxdeg <= GIK_FAST_ROWS) {
@@ -270,6 +314,9 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->deg, deg.data(), deg.size());
     ok = ok && !upload(&p->fast_info, finfo.data(), finfo.size());
     ok = ok && !upload(&p->fast_target, ftarget.data(), ftarget.size());
+    ok = ok && !upload(&p->fast2_info, f2info.data(), f2info.size());
+    ok = ok && !upload(&p->fast2_target, f2target.data(), f2target.size());
+    ok = ok && !upload(&p->fast2_node, f2node.data(), f2node.size());
     ok = ok && !upload(&p->duo_info, dinfo.data(), dinfo.size());
     ok = ok && !upload(&p->duo_target, dtarget.data(), dtarget.size());
     ok = ok && !upload(&p->dense_target, dense_t.data(), dense_t.size());
@@ -301,7 +348,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_goal_i, p->dense_goal_j,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_goal_i, p->dense_goal_j,
                     p->dense_goal_slot, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};

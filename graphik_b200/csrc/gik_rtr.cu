@@ -407,7 +407,8 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
     if (force && force[0] == '1') kernel = GIK_KERNEL_GENERIC;
     if (kernel == GIK_KERNEL_AUTO) {
         if (p->N <= 32) kernel = (B >= 16384 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
-        else kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE : GIK_KERNEL_GENERIC;
+        else kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE
+                      : (p->fast2_info ? GIK_KERNEL_LATENCY : GIK_KERNEL_GENERIC);
     }
     if (kernel == GIK_KERNEL_DENSE) {
         const int rc = gik_launch_rtr_cta(p, a, st);
@@ -420,7 +421,9 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
         kernel = GIK_KERNEL_LATENCY;   // no lock-step specialisation for this plan
     }
     if (kernel == GIK_KERNEL_LATENCY) {
-        const int rc = gik_launch_rtr_fast(p, a, st);
+        int rc = gik_launch_rtr_fast(p, a, st);
+        if (rc <= 0) return rc;
+        rc = gik_launch_rtr_fast2(p, a, st);   // 33 .. 64 nodes: two nodes per lane
         if (rc <= 0) return rc;
     }
     if (p->W == 16) return launch_rtr<16, 1>(p, a, st);

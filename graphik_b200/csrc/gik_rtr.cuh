@@ -25,6 +25,8 @@ struct RtrArgs {
 // gik_rtr_fast.cu: one warp per problem, slot data cached in registers (N <= 32).
 // Returns GIK_OK, or 1 if no specialisation covers the plan (caller falls back to k_rtr).
 int gik_launch_rtr_fast(const GikPlan *p, RtrArgs &a, cudaStream_t st);
+// gik_rtr_fast.cu: one warp per problem, two nodes per lane, slot cache in shared memory (32 < N <= 64, sparse).
+int gik_launch_rtr_fast2(const GikPlan *p, RtrArgs &a, cudaStream_t st);
 // gik_rtr_duo.cu: two problems per warp in lock-step (N <= 16); same return convention.
 int gik_launch_rtr_duo(const GikPlan *p, RtrArgs &a, cudaStream_t st);
 // gik_rtr_cta.cu: one CTA per problem with a dense target matrix (32 < N <= 128); same convention.

@@ -403,6 +403,375 @@ int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     return gik_check_cuda(cudaGetLastError(), "k_rtr_fast launch");
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// 33 .. 64 nodes, sparse (e.g. the 20-DOF chain of BASELINE configs[3]: N = 44, 115 terms, degree 5..7):
+// one warp per problem, TWO nodes per lane.  The plan orders the nodes by degree: the 32 highest-degree
+// nodes are every lane's first node (S0 slots), the rest the second node of lanes 0 .. N-33 (S1 slots),
+// so a lane walks S0 + S1 slots instead of the 2 * maxdeg of a fixed l / l+32 assignment.  Slot cache in
+// shared memory ([slot][4][lane], conflict-free; loads independent of delta), node state in registers.
+template <int S0, int S1>
+__device__ __forceinline__ void rtr_fast2_body(const RtrArgs &a, const uint32_t *__restrict__ info_tbl,
+                                               const double *__restrict__ target_tbl,
+                                               const int32_t *__restrict__ node_tbl)
+{
+    constexpr int ST = S0 + S1;
+    constexpr int NPW = 64;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int goal_pad = (a.n_goal + 1) & ~1;
+    double *P = smem;
+    double *V = P + 3 * NPW;
+    double *goal = V + 3 * NPW;
+    double *tgt = goal + goal_pad + lane;   // [ST][32] per-problem targets of this lane's slots
+    double *scm = tgt + ST * 32;            // [ST][4][32] slot cache
+    const GikSolveOpts &o = a.o;
+    const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
+
+    // this lane's nodes; a lane without a second node parks it on the unused exchange slot 63
+    int nd[2];
+    bool valid[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int t = node_tbl[m * 32 + lane];
+        valid[m] = t >= 0;
+        nd[m] = valid[m] ? t : NPW - 1;
+    }
+    uint32_t info[ST];
+#pragma unroll
+    for (int s = 0; s < ST; ++s) info[s] = info_tbl[s * 32 + lane];
+
+    auto publish = [&](double *buf, const double (&v)[2][3]) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            buf[nd[m]] = v[m][0]; buf[NPW + nd[m]] = v[m][1]; buf[2 * NPW + nd[m]] = v[m][2];
+        }
+    };
+
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(a.work_counter, 1);
+        b = __shfl_sync(GIK_FULL_MASK, b, 0, 32);
+        if (b >= a.B) break;
+
+        double x[2][3], g[2][3], eta[2][3], Heta[2][3], r[2][3], dl[2][3], Hd[2][3];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            x[m][0] = 0.0; x[m][1] = 0.0; x[m][2] = 0.0;
+            if (valid[m]) {
+                const double *src = a.Y_init + ((size_t)b * a.N + nd[m]) * 3;
+                x[m][0] = src[0]; x[m][1] = src[1]; x[m][2] = src[2];
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < a.n_goal; k += 32) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
+        publish(P, x);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < ST; ++s) {
+            const uint32_t gs = GIK_SLOT_GOAL(info[s]);
+            tgt[s * 32] = gs ? goal[gs - 1] : target_tbl[s * 32 + lane];
+        }
+
+        // cost / gradient at point p (published in P) + rebuild of the slot cache
+        auto rebuild = [&](const double (&p)[2][3], double (&gout)[2][3]) -> double {
+            double fpart = 0.0;
+            double ga[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+            for (int s = 0; s < ST; ++s) {
+                const int m = s < S0 ? 0 : 1;
+                const int j = GIK_SLOT_NBR(info[s]);
+                const uint32_t kind = GIK_SLOT_KIND(info[s]);
+                const double dx = p[m][0] - P[j], dy = p[m][1] - P[NPW + j], dz = p[m][2] - P[2 * NPW + j];
+                const double d = dx * dx + dy * dy + dz * dz;
+                double rr = d - tgt[s * 32];
+                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
+                                 ((kind == GIK_TERM_UP) & (rr > 0.0));
+                rr = act ? rr : 0.0;
+                fpart = fma(rr, rr, fpart);
+                ga[m][0] = fma(rr, dx, ga[m][0]);
+                ga[m][1] = fma(rr, dy, ga[m][1]);
+                ga[m][2] = fma(rr, dz, ga[m][2]);
+                const double two = act ? 2.0 : 0.0;
+                scm[(s * 4 + 0) * 32] = two * dx; scm[(s * 4 + 1) * 32] = two * dy;
+                scm[(s * 4 + 2) * 32] = two * dz; scm[(s * 4 + 3) * 32] = 2.0 * rr;
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                gout[m][0] = 2.0 * ga[m][0]; gout[m][1] = 2.0 * ga[m][1]; gout[m][2] = 2.0 * ga[m][2];
+            }
+            return 0.5 * fpart;
+        };
+
+        double fx, gg, Mi[6];
+        {
+            double v[8];
+            v[0] = rebuild(x, g);
+            v[1] = 0.0;
+#pragma unroll
+            for (int k = 2; k < 8; ++k) v[k] = 0.0;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                v[1] = fma(g[m][0], g[m][0], fma(g[m][1], g[m][1], fma(g[m][2], g[m][2], v[1])));
+                v[2] = fma(x[m][0], x[m][0], v[2]); v[3] = fma(x[m][0], x[m][1], v[3]);
+                v[4] = fma(x[m][0], x[m][2], v[4]); v[5] = fma(x[m][1], x[m][1], v[5]);
+                v[6] = fma(x[m][1], x[m][2], v[6]); v[7] = fma(x[m][2], x[m][2], v[7]);
+            }
+            node_allreduce<1, 8>(v);
+            fx = v[0];
+            gg = v[1];
+            gik_sylvester_inverse(v + 2, Mi);
+        }
+        double norm_grad = sqrt(gg);
+        double Delta = o.Delta0;
+        int k_outer = 0, inner_total = 0, status = GIK_STATUS_MAXITER;
+        if (!(isfinite(fx) && isfinite(gg))) {
+            status = GIK_STATUS_NAN;
+        } else {
+            for (;;) {
+                // ================= tCG (trust_region.py:436-599), eta0 = 0, precon = identity
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        eta[m][q] = 0.0; Heta[m][q] = 0.0; r[m][q] = g[m][q]; dl[m][q] = -g[m][q];
+                    }
+                }
+                double e_Pe = 0.0, r_r = gg;
+                const double norm_r0 = sqrt(r_r);
+                double z_r = r_r, d_Pd = r_r, e_Pd = 0.0, model_value = 0.0;
+                const double pw = o.theta == 1.0 ? norm_r0 : pow(norm_r0, o.theta);
+                const double r_target = norm_r0 * fmin(pw, o.kappa);
+                const double r_target2 = r_target * r_target;   // <r,r> <= target^2 (sqrt is monotone)
+                const double Delta2 = Delta * Delta;
+                double inv_z_r = gik_rcp(z_r);
+                int stop = MAX_INNER_ITER;
+                int j = 0;
+                for (j = 0; j < o.maxinner; ++j) {
+                    // ---- Hdelta = proj(x, lhess(x, delta))
+                    publish(V, dl);
+                    __syncwarp();
+                    double z[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, zb[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+                    for (int s = 0; s < ST; ++s) {
+                        const int m = s < S0 ? 0 : 1;
+                        const int jn = GIK_SLOT_NBR(info[s]);
+                        const double wx = dl[m][0] - V[jn], wy = dl[m][1] - V[NPW + jn], wz = dl[m][2] - V[2 * NPW + jn];
+                        const double cx = scm[(s * 4 + 0) * 32], cy = scm[(s * 4 + 1) * 32];
+                        const double cz = scm[(s * 4 + 2) * 32], c2 = scm[(s * 4 + 3) * 32];
+                        const double t = fma(cx, wx, fma(cy, wy, cz * wz));
+                        z[m][0] = fma(c2, wx, z[m][0]);
+                        z[m][1] = fma(c2, wy, z[m][1]);
+                        z[m][2] = fma(c2, wz, z[m][2]);
+                        zb[m][0] = fma(t, cx, zb[m][0]);
+                        zb[m][1] = fma(t, cy, zb[m][1]);
+                        zb[m][2] = fma(t, cz, zb[m][2]);
+                    }
+                    double v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        z[m][0] += zb[m][0]; z[m][1] += zb[m][1]; z[m][2] += zb[m][2];
+                        v[0] += dl[m][0] * z[m][0] + dl[m][1] * z[m][1] + dl[m][2] * z[m][2];
+                        v[1] += z[m][1] * x[m][2] - z[m][2] * x[m][1];      // c = sum Z_i x Y_i
+                        v[2] += z[m][2] * x[m][0] - z[m][0] * x[m][2];
+                        v[3] += z[m][0] * x[m][1] - z[m][1] * x[m][0];
+                        v[4] += dl[m][1] * x[m][2] - dl[m][2] * x[m][1];    // u = sum delta_i x Y_i
+                        v[5] += dl[m][2] * x[m][0] - dl[m][0] * x[m][2];
+                        v[6] += dl[m][0] * x[m][1] - dl[m][1] * x[m][0];
+                    }
+                    node_allreduce_t<1, 8>(v, lane);
+                    double om[3];
+                    gik_sym_mul(Mi, v + 1, om);
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        Hd[m][0] = z[m][0] - (x[m][1] * om[2] - x[m][2] * om[1]);
+                        Hd[m][1] = z[m][1] - (x[m][2] * om[0] - x[m][0] * om[2]);
+                        Hd[m][2] = z[m][2] - (x[m][0] * om[1] - x[m][1] * om[0]);
+                    }
+                    const double d_Hd = v[0] - (om[0] * v[4] + om[1] * v[5] + om[2] * v[6]);
+                    ++inner_total;
+                    const double alpha = gik_div(z_r, d_Hd, gik_rcp(d_Hd));
+                    const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+                    if (!(d_Hd > 0.0) || e_Pe_new >= Delta2) {   // also catches NaN
+                        const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                eta[m][q] = fma(tau, dl[m][q], eta[m][q]);
+                                Heta[m][q] = fma(tau, Hd[m][q], Heta[m][q]);
+                            }
+                        }
+                        stop = d_Hd <= 0.0 ? NEGATIVE_CURVATURE : EXCEEDED_TR;
+                        break;
+                    }
+                    e_Pe = e_Pe_new;
+                    double ne[2][3], nh[2][3], nr[2][3], sdot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            ne[m][q] = fma(alpha, dl[m][q], eta[m][q]);
+                            nh[m][q] = fma(alpha, Hd[m][q], Heta[m][q]);
+                            nr[m][q] = fma(alpha, Hd[m][q], r[m][q]);
+                            sdot[0] = fma(ne[m][q], g[m][q], sdot[0]);
+                            sdot[1] = fma(ne[m][q], nh[m][q], sdot[1]);
+                            sdot[2] = fma(nr[m][q], nr[m][q], sdot[2]);
+                        }
+                    }
+                    node_allreduce_t<1, 4>(sdot, lane);
+                    const double new_model_value = sdot[0] + 0.5 * sdot[1];
+                    if (new_model_value >= model_value) {
+                        stop = MODEL_INCREASED;
+                        break;
+                    }
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { eta[m][q] = ne[m][q]; Heta[m][q] = nh[m][q]; r[m][q] = nr[m][q]; }
+                    }
+                    model_value = new_model_value;
+                    r_r = sdot[2];
+                    if (j >= o.mininner && r_r <= r_target2) {
+                        stop = o.kappa < pw ? REACHED_TARGET_LINEAR : REACHED_TARGET_SUPERLINEAR;
+                        break;
+                    }
+                    const double beta = gik_div(r_r, z_r, inv_z_r);
+                    z_r = r_r;
+                    inv_z_r = gik_rcp(z_r);
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) dl[m][q] = fma(beta, dl[m][q], -r[m][q]);
+                    }
+                    e_Pd = beta * (e_Pd + alpha * d_Pd);
+                    d_Pd = z_r + beta * beta * d_Pd;
+                }
+                const int numit = j < o.maxinner ? j : o.maxinner - 1;
+
+                // ================= proposal x + eta; dl <- x_prop, Hd <- grad(x_prop), cache <- x_prop
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) dl[m][q] = x[m][q] + eta[m][q];
+                }
+                __syncwarp();
+                publish(P, dl);
+                __syncwarp();
+                double v[10];
+                v[0] = rebuild(dl, Hd);
+#pragma unroll
+                for (int k = 1; k < 10; ++k) v[k] = 0.0;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    v[1] += g[m][0] * eta[m][0] + g[m][1] * eta[m][1] + g[m][2] * eta[m][2];
+                    v[2] += eta[m][0] * Heta[m][0] + eta[m][1] * Heta[m][1] + eta[m][2] * Heta[m][2];
+                    v[3] += Hd[m][0] * Hd[m][0] + Hd[m][1] * Hd[m][1] + Hd[m][2] * Hd[m][2];
+                    v[4] = fma(dl[m][0], dl[m][0], v[4]); v[5] = fma(dl[m][0], dl[m][1], v[5]);
+                    v[6] = fma(dl[m][0], dl[m][2], v[6]); v[7] = fma(dl[m][1], dl[m][1], v[7]);
+                    v[8] = fma(dl[m][1], dl[m][2], v[8]); v[9] = fma(dl[m][2], dl[m][2], v[9]);
+                }
+                node_allreduce<1, 10>(v);
+                const double fx_prop = v[0];
+                double rhonum = fx - fx_prop;
+                double rhoden = -v[1] - 0.5 * v[2];
+                const double rho_reg = fmax(1.0, fabs(fx)) * eps * o.rho_regularization;
+                rhonum += rho_reg;
+                rhoden += rho_reg;
+                const bool model_decreased = rhoden >= 0.0;
+                const double rho = rhonum / rhoden;
+                const double Delta_used = Delta;
+                if (rho < 0.25 || !model_decreased || isnan(rho)) {
+                    Delta = Delta / 4.0;
+                } else if (rho > 0.75 && (stop == NEGATIVE_CURVATURE || stop == EXCEEDED_TR)) {
+                    Delta = fmin(2.0 * Delta, o.Delta_bar);
+                }
+                const bool accept = model_decreased && rho > o.rho_prime;
+                if (accept) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { x[m][q] = dl[m][q]; g[m][q] = Hd[m][q]; }
+                    }
+                    fx = fx_prop;
+                    gg = v[3];
+                    norm_grad = sqrt(gg);
+                    gik_sylvester_inverse(v + 4, Mi);
+                } else {
+                    // rejected: bring the exchange buffer and the slot cache back to x
+                    __syncwarp();
+                    publish(P, x);
+                    __syncwarp();
+                    double gtmp[2][3];
+                    rebuild(x, gtmp);
+                }
+                if (a.trace && k_outer < a.trace_rows && lane == 0) {
+                    double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
+                    row[0] = Delta_used;
+                    row[1] = (double)numit;
+                    row[2] = (double)stop;
+                    row[3] = fx_prop;
+                    row[4] = accept ? 1.0 : 0.0;
+                    row[5] = accept ? norm_grad : nan("");
+                }
+                ++k_outer;
+                if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
+                if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (valid[m]) {
+                double *dst = a.Y_out + ((size_t)b * a.N + nd[m]) * 3;
+                dst[0] = x[m][0]; dst[1] = x[m][1]; dst[2] = x[m][2];
+            }
+        }
+        if (lane == 0) {
+            a.f[b] = fx;
+            a.gradnorm[b] = norm_grad;
+            a.iters[b] = k_outer;
+            a.status[b] = status;
+            if (a.n_inner) a.n_inner[b] = inner_total;
+        }
+        __syncwarp();
+    }
+}
+
+// 254 registers without spills (8 warps / SM) against 168 with ~20 spilled doubles (11 warps / SM, shared-memory bound)
+#ifndef GIK_FAST2_MINB
+#define GIK_FAST2_MINB 8
+#endif
+template <int S0, int S1>
+__global__ void __launch_bounds__(kThreads, GIK_FAST2_MINB) k_rtr_fast2(const RtrArgs a, const uint32_t *__restrict__ info_tbl,
+                                                            const double *__restrict__ target_tbl,
+                                                            const int32_t *__restrict__ node_tbl)
+{
+    rtr_fast2_body<S0, S1>(a, info_tbl, target_tbl, node_tbl);
+}
+
+template <int S0, int S1>
+int launch2(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+{
+    auto kern = k_rtr_fast2<S0, S1>;
+    constexpr int ST = S0 + S1;
+    const int goal_pad = (p->n_goal + 1) & ~1;
+    const size_t smem = (size_t)(6 * 64 + goal_pad + ST * 32 + ST * 128) * sizeof(double);
+    if (smem > 227 * 1024) return 1;
+    if (smem > 48 * 1024)
+        GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = p->sm_count * per_sm;
+    if (blocks > a.B) blocks = a.B;
+    GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
+    kern<<<blocks, kThreads, smem, st>>>(a, p->fast2_info, p->fast2_target, p->fast2_node);
+    return gik_check_cuda(cudaGetLastError(), "k_rtr_fast2 launch");
+}
+
 }  // namespace
 
 int gik_launch_rtr_fast(const GikPlan *p, RtrArgs &a, cudaStream_t st)
@@ -423,6 +792,20 @@ int gik_launch_rtr_fast(const GikPlan *p, RtrArgs &a, cudaStream_t st)
         case 9: return launch<1, 9>(p, a, st);
         case 10: return launch<1, 10>(p, a, st);
         case 11: case 12: return launch<1, 12>(p, a, st);
+        default: return 1;
+    }
+}
+
+// 33 .. 64 nodes, two nodes per lane.  The tables are laid out for the instantiated (S0, S1) the plan chose.
+int gik_launch_rtr_fast2(const GikPlan *p, RtrArgs &a, cudaStream_t st)
+{
+    if (!p->fast2_info) return 1;
+    switch (p->fast2_S0 * 16 + p->fast2_S1) {
+        case 6 * 16 + 5: return launch2<6, 5>(p, a, st);
+        case 8 * 16 + 5: return launch2<8, 5>(p, a, st);
+        case 8 * 16 + 8: return launch2<8, 8>(p, a, st);
+        case 12 * 16 + 8: return launch2<12, 8>(p, a, st);
+        case 12 * 16 + 12: return launch2<12, 12>(p, a, st);
         default: return 1;
     }
 }
