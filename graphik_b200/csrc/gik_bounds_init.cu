@@ -20,15 +20,19 @@
 // reads from the LOWER triangle of the non-symmetric factor; the K x K scatter matrix
 // of the linear projection) are solved by a CTA-parallel cyclic Jacobi iteration
 // (round-robin pair ordering, N/2 disjoint rotations per step) in shared memory.
+#include <cstdio>
+#include <cstdlib>
+
 #include "gik_common.cuh"
 
 namespace {
 
 struct BiArgs {
-    int N, n_goal, n_goal_edges, n_omega_edges;
+    int N, n_goal, n_goal_edges, n_omega_edges, goal_p, goal_q;
     const double *bs_lower, *bs_upper;
     const int32_t *goal_edge_i, *goal_edge_j, *goal_edge_slot;
     const int32_t *omega_i, *omega_j;
+    const int32_t *omega_ptr, *omega_adj;   // CSR of omega (both directions)
     const double *goal_d2;   // [B][n_goal] (bounds from goals) or null
     const double *lb_in, *ub_in;  // [B][N][N] (init from given bounds) or null
     int B;
@@ -58,10 +62,30 @@ __device__ __forceinline__ double block_sum(double v, double *red)
     return red[32];
 }
 
+#ifdef GIK_BI_PROFILE
+#define BI_TICK(name) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0 && b == 0) { long long t1 = clock64(); printf("bi_profile %-10s %10lld cycles\n", name, t1 - t0); t0 = clock64(); } } while (0)
+#else
+#define BI_TICK(name)
+#endif
+
+__device__ __forceinline__ int pow2_at_least(int n, int cap)
+{
+    int t = 1;
+    while (t < n && t < cap) t <<= 1;
+    return t;
+}
+
 // Cyclic Jacobi for the symmetric n x n matrix A (leading dimension ld), in place:
 // on exit diag(A) holds the eigenvalues and, if V != null, the columns of V the
-// eigenvectors.  cs: 2 * (n/2 + 1) doubles, red: 33 doubles of shared memory.
-__device__ void jacobi_eig(double *A, double *V, int n, int ld, double *cs, double *red)
+// eigenvectors.  cs: 2 * (n/2 + 1) doubles, pq: n/2 + 1 ints, red: 33 doubles of shared memory.
+//
+// One step applies the n/2 disjoint rotations of a round-robin pairing.  Threads are mapped in 2-D so
+// that a thread's rotation (p, q, c, s) is fixed for the whole phase and no per-element index arithmetic
+// remains (the first version spent ~150 instructions per element on k / half, k % half and two
+// runtime modulos: 39 k cycles per step at n = 118):
+//   column phase  A <- A J, V <- V J : thread = (pair t, row group)   -> elements (i, p), (i, q)
+//   row phase     A <- J^T A         : thread = (column j, pair group) -> elements (p, j), (q, j)
+__device__ void jacobi_eig(double *A, double *V, int n, int ld, double *cs, int *pq, double *red)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (V) {
@@ -71,82 +95,98 @@ __device__ void jacobi_eig(double *A, double *V, int n, int ld, double *cs, doub
     if (n < 2) return;
     const int ne = n + (n & 1);
     const int half = ne / 2;
+    const int TT = pow2_at_least(half, nt), RG = nt / TT;     // column phase: pair index x row groups
+    const int tt = tid & (TT - 1), ti = tid / TT;
+    const int TJ = pow2_at_least(n, nt), PG = nt / TJ;        // row phase: column index x pair groups
+    const int tj = tid & (TJ - 1), tg = tid / TJ;
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, tot = 0.0;
-        for (int k = tid; k < n * n; k += nt) {
-            const int i = k / n, j = k % n;
-            const double a = A[i * ld + j];
-            tot += a * a;
-            if (i != j) off += a * a;
+        for (int i = tg; i < n; i += PG) {
+            for (int j = tj; j < n; j += TJ) {
+                const double a = A[i * ld + j];
+                tot += a * a;
+                if (i != j) off += a * a;
+            }
         }
         off = block_sum(off, red);
         tot = block_sum(tot, red);
+#ifdef GIK_BI_PROFILE
+        if (blockIdx.x == 0 && tid == 0) printf("bi_profile   sweep %d n %d off/tot %.3e\n", sweep, n, off / tot);
+#endif
         if (off <= 1e-33 * tot || tot == 0.0) break;
         for (int step = 0; step < ne - 1; ++step) {
-            // rotation angles of this step's disjoint pairs
+            // rotation angles of this step's disjoint pairs; the pairs of the previous step are now
+            // exactly diagonal (no pair repeats inside a sweep, so these writes touch nobody's reads)
             for (int t = tid; t < half; t += nt) {
+                if (step > 0) {
+                    const int old = pq[t];
+                    if (old >= 0 && cs[2 * t + 1] != 0.0) {
+                        const int p0 = old & 0xffff, q0 = old >> 16;
+                        A[p0 * ld + q0] = 0.0;
+                        A[q0 * ld + p0] = 0.0;
+                    }
+                }
                 int p, q;
                 if (t == 0) { p = ne - 1; q = step; }
                 else { p = (step + t) % (ne - 1); q = (step - t + (ne - 1)) % (ne - 1); }
                 double c = 1.0, s = 0.0;
-                if (p < n && q < n) {
+                const bool real = p < n && q < n;
+                if (real) {
                     const double apq = A[p * ld + q];
                     if (apq != 0.0) {
                         const double theta = (A[q * ld + q] - A[p * ld + p]) / (2.0 * apq);
-                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(tt * tt + 1.0);
-                        s = tt * c;
+                        const double tt2 = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt2 * tt2 + 1.0);
+                        s = tt2 * c;
                     }
                 }
                 cs[2 * t] = c;
                 cs[2 * t + 1] = s;
+                pq[t] = real ? (p | (q << 16)) : -1;
             }
             __syncthreads();
             // A <- A J (and V <- V J): columns p, q of every row
-            for (int k = tid; k < n * half; k += nt) {
-                const int i = k / half, t = k % half;
-                int p, q;
-                if (t == 0) { p = ne - 1; q = step; }
-                else { p = (step + t) % (ne - 1); q = (step - t + (ne - 1)) % (ne - 1); }
-                if (p >= n || q >= n) continue;
+            for (int t = tt; t < half; t += TT) {
+                const int code = pq[t];
                 const double c = cs[2 * t], s = cs[2 * t + 1];
-                if (s == 0.0) continue;
-                const double aip = A[i * ld + p], aiq = A[i * ld + q];
-                A[i * ld + p] = c * aip - s * aiq;
-                A[i * ld + q] = s * aip + c * aiq;
-                if (V) {
-                    const double vip = V[i * ld + p], viq = V[i * ld + q];
-                    V[i * ld + p] = c * vip - s * viq;
-                    V[i * ld + q] = s * vip + c * viq;
+                if (code < 0 || s == 0.0) continue;
+                const int p = code & 0xffff, q = code >> 16;
+                for (int i = ti; i < n; i += RG) {
+                    const double aip = A[i * ld + p], aiq = A[i * ld + q];
+                    A[i * ld + p] = c * aip - s * aiq;
+                    A[i * ld + q] = s * aip + c * aiq;
+                    if (V) {
+                        const double vip = V[i * ld + p], viq = V[i * ld + q];
+                        V[i * ld + p] = c * vip - s * viq;
+                        V[i * ld + q] = s * vip + c * viq;
+                    }
                 }
             }
             __syncthreads();
             // A <- J^T A: rows p, q of every column
-            for (int k = tid; k < n * half; k += nt) {
-                const int j = k % n, t = k / n;
-                int p, q;
-                if (t == 0) { p = ne - 1; q = step; }
-                else { p = (step + t) % (ne - 1); q = (step - t + (ne - 1)) % (ne - 1); }
-                if (p >= n || q >= n) continue;
+            for (int t = tg; t < half; t += PG) {
+                const int code = pq[t];
                 const double c = cs[2 * t], s = cs[2 * t + 1];
-                if (s == 0.0) continue;
-                const double apj = A[p * ld + j], aqj = A[q * ld + j];
-                A[p * ld + j] = c * apj - s * aqj;
-                A[q * ld + j] = s * apj + c * aqj;
-            }
-            __syncthreads();
-            // the rotated pair is now exactly diagonal
-            for (int t = tid; t < half; t += nt) {
-                int p, q;
-                if (t == 0) { p = ne - 1; q = step; }
-                else { p = (step + t) % (ne - 1); q = (step - t + (ne - 1)) % (ne - 1); }
-                if (p < n && q < n && cs[2 * t + 1] != 0.0) {
-                    A[p * ld + q] = 0.0;
-                    A[q * ld + p] = 0.0;
+                if (code < 0 || s == 0.0) continue;
+                const int p = code & 0xffff, q = code >> 16;
+                for (int j = tj; j < n; j += TJ) {
+                    const double apj = A[p * ld + j], aqj = A[q * ld + j];
+                    A[p * ld + j] = c * apj - s * aqj;
+                    A[q * ld + j] = s * apj + c * aqj;
                 }
             }
             __syncthreads();
         }
+        // the last step's pairs
+        for (int t = tid; t < half; t += nt) {
+            const int old = pq[t];
+            if (old >= 0 && cs[2 * t + 1] != 0.0) {
+                const int p0 = old & 0xffff, q0 = old >> 16;
+                A[p0 * ld + q0] = 0.0;
+                A[q0 * ld + p0] = 0.0;
+            }
+        }
+        __syncthreads();
     }
     __syncthreads();
 }
@@ -171,13 +211,17 @@ __global__ void k_bounds_init(const BiArgs a)
 {
     extern __shared__ double smem[];
     const int N = a.N, NN = N * N, tid = threadIdx.x, nt = blockDim.x;
-    // small arrays first
+    // small arrays first (sizes: gik_bi_small_doubles in gik_common.cuh)
     double *cs = smem;                 // 2*(N/2+1) <= N+2
     double *red = cs + (N + 2);        // 33
     double *lam = red + 34;            // N   eigenvalues / row buffer
     double *rowM = lam + N;            // N
-    int *order = reinterpret_cast<int *>(rowM + N);  // N ints
-    double *mats = rowM + N + (N + 1) / 2 + 1;
+    double *Lp = rowM + N;             // N   LOWER of the pairs (., p_n) of this goal
+    double *Lq = Lp + N;               // N   LOWER of the pairs (., q_n)
+    double *part = Lq + N;             // 2 * 128 partial maxima of the two halves of a max-plus row
+    int *order = reinterpret_cast<int *>(part + 256);  // N ints
+    int *pq = order + N + (N & 1);     // N/2 + 1 ints: rotation pairs of the current Jacobi step
+    double *mats = smem + gik_bi_small_doubles(N);
     double *M1, *M2, *M3;
     if (a.use_scratch == 2) {          // nothing fits: all three matrices in global scratch
         M1 = a.scratch + (size_t)blockIdx.x * 3 * NN;
@@ -191,6 +235,9 @@ __global__ void k_bounds_init(const BiArgs a)
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
+#ifdef GIK_BI_PROFILE
+        long long t0 = clock64();
+#endif
         double *Up = M1, *D = M2;
         if (a.do_bounds) {
             // ---------------- bound smoothing
@@ -205,38 +252,72 @@ __global__ void k_bounds_init(const BiArgs a)
             }
             __syncthreads();
             // min-plus closure (Floyd-Warshall); row k / column k are fixed points of step k
+            const int TJ = pow2_at_least(N, nt), G = nt / TJ;   // thread = (column, row group)
+            const int tj = tid & (TJ - 1), tg = tid / TJ;
             for (int k = 0; k < N; ++k) {
-                for (int e = tid; e < NN; e += nt) {
-                    const int i = e / N, j = e % N;
-                    const double via = Up[i * N + k] + Up[k * N + j];
-                    if (via < Up[e]) Up[e] = via;
+                for (int i = tg; i < N; i += G) {
+                    const double uik = Up[i * N + k];
+                    for (int j = tj; j < N; j += TJ) {
+                        const double via = uik + Up[k * N + j];
+                        if (via < Up[i * N + j]) Up[i * N + j] = via;
+                    }
                 }
                 __syncthreads();
             }
-            // lower bounds row by row: rowM[b] = max_a (L[a,b] - Up[u,a]); lower[u,v] = max_b (rowM[b] - Up[b,v])
+            BI_TICK("floyd");
+            // LOWER of this goal: the static table, except the pairs with p_n / q_n (rows Lp, Lq), which hold
+            // the goal's exact distances on the goal edges (their static entries are 0)
+            const int gp = a.goal_p, gq = a.goal_q;
+            for (int i = tid; i < N; i += nt) {
+                Lp[i] = gp >= 0 ? a.bs_lower[i * N + gp] : 0.0;
+                Lq[i] = gq >= 0 ? a.bs_lower[i * N + gq] : 0.0;
+            }
+            __syncthreads();
+            for (int e = tid; e < a.n_goal_edges; e += nt) {
+                const int i = a.goal_edge_i[e], j = a.goal_edge_j[e];
+                const double l = sqrt(gd[a.goal_edge_slot[e]]);
+                if (j == gp) Lp[i] = l; else if (i == gp) Lp[j] = l;
+                if (j == gq) Lq[i] = l; else if (i == gq) Lq[j] = l;
+            }
+            __syncthreads();
+            // lower bounds row by row, two max-plus products (max is exact, so any split gives the same bits):
+            //   rowM[b] = max(-Up[u,b], max_{a: L[a,b] > 0} (L[a,b] - Up[u,a]));  lower[u,v] = max(0, max_b (rowM[b] - Up[b,v]))
+            // thread = (column, half of the contraction range)
+            const int H = G < 2 ? 1 : 2;
+            const int th = tg;               // which half (threads with tg >= H idle in these loops)
+            const int chunk = (N + H - 1) / H;
             for (int u = 0; u < N; ++u) {
+                if (th < H) {
+                    const int a0 = th * chunk, a1 = min(N, a0 + chunk);
+                    for (int bb = tj; bb < N; bb += TJ) {
+                        double m = -INFINITY;
+                        for (int aa = a0; aa < a1; ++aa) {
+                            const double l = bb == gp ? Lp[aa] : (bb == gq ? Lq[aa] :
+                                             (aa == gp ? Lp[bb] : (aa == gq ? Lq[bb] : a.bs_lower[aa * N + bb])));
+                            if (l > 0.0) m = fmax(m, l - Up[u * N + aa]);
+                        }
+                        part[th * 128 + bb] = m;
+                    }
+                }
+                __syncthreads();
                 for (int bb = tid; bb < N; bb += nt) {
                     double m = -Up[u * N + bb];  // joining arc b -> b' of weight 0
-                    for (int aa = 0; aa < N; ++aa) {
-                        const double l = a.bs_lower[aa * N + bb];
-                        if (l > 0.0) m = fmax(m, l - Up[u * N + aa]);
-                    }
+                    for (int h = 0; h < H; ++h) m = fmax(m, part[h * 128 + bb]);
                     rowM[bb] = m;
                 }
                 __syncthreads();
-                // goal edges: L[i,j] = L[j,i] = sqrt(goal_d2); only 2 * n_anchor of them -> folded serially
-                if (tid == 0) {
-                    for (int e = 0; e < a.n_goal_edges; ++e) {
-                        const int i = a.goal_edge_i[e], j = a.goal_edge_j[e];
-                        const double l = sqrt(gd[a.goal_edge_slot[e]]);
-                        rowM[j] = fmax(rowM[j], l - Up[u * N + i]);
-                        rowM[i] = fmax(rowM[i], l - Up[u * N + j]);
+                if (th < H) {
+                    const int b0 = th * chunk, b1 = min(N, b0 + chunk);
+                    for (int v = tj; v < N; v += TJ) {
+                        double m = 0.0;
+                        for (int bb = b0; bb < b1; ++bb) m = fmax(m, rowM[bb] - Up[bb * N + v]);
+                        part[th * 128 + v] = m;
                     }
                 }
                 __syncthreads();
                 for (int v = tid; v < N; v += nt) {
-                    double m = 0.0;
-                    for (int bb = 0; bb < N; ++bb) m = fmax(m, rowM[bb] - Up[bb * N + v]);
+                    double m = part[v];
+                    for (int h = 1; h < H; ++h) m = fmax(m, part[h * 128 + v]);
                     const double lo = (u == v) ? 0.0 : m;
                     const double up = Up[u * N + v];
                     if (a.lb_out) a.lb_out[(size_t)b * NN + u * N + v] = lo;
@@ -254,6 +335,7 @@ __global__ void k_bounds_init(const BiArgs a)
             }
             __syncthreads();
         }
+        BI_TICK("lower");
         if (!a.Y_init) continue;
 
         // ---------------- Gram matrix B = -1/2 J D J  (dgp.py:28-31), in place in D
@@ -289,7 +371,9 @@ __global__ void k_bounds_init(const BiArgs a)
         }
         __syncthreads();
         // ---------------- factor (dgp.py:150-159): X = V sqrt(max(lambda,0)), columns by descending lambda
-        jacobi_eig(G, V, N, N, cs, red);
+        BI_TICK("gram");
+        jacobi_eig(G, V, N, N, cs, pq, red);
+        BI_TICK("eig_gram");
         // Eigenvector signs are arbitrary, yet the rank heuristic below is NOT invariant to them
         // (it reads a triangle of the non-symmetric factor).  The reference inherits whatever
         // LAPACK returns; here the sign is fixed canonically: the entry of largest magnitude of
@@ -320,24 +404,51 @@ __global__ void k_bounds_init(const BiArgs a)
             Aw[k] = i >= j ? X[i * N + j] : X[j * N + i];
         }
         __syncthreads();
-        jacobi_eig(Aw, nullptr, N, N, cs, red);
+        BI_TICK("factor");
+        jacobi_eig(Aw, nullptr, N, N, cs, pq, red);
+        BI_TICK("eig_rank");
         double cnt = 0.0;
         for (int i = tid; i < N; i += nt) cnt += Aw[i * N + i] > 1e-8 ? 1.0 : 0.0;
         int K = (int)(block_sum(cnt, red) + 0.5);
         if (K > N) K = N;
         // ---------------- linear_projection (dgp.py:174-183): S = sum_{omega} (P_i-P_j)(P_i-P_j)^T, P = X[:, :K]
-        double *S = M1, *E = M3;
+        // evaluated node-wise: W_i = sum_{j ~ i} (P_i - P_j) (N x K, kept where E will go), S = 2 sum_i P_i^T W_i
+        // (the K^2 |omega| edge-wise evaluation cost 5 M cycles per goal at N = 118, K = 40), then symmetrised
+        double *S = M1, *E = M3, *Wn = M3;
+        {
+            // thread = (coordinate r, node group); fixed neighbour order -> deterministic sums
+            const int TK = pow2_at_least(K, nt), GK = nt / TK;
+            const int tr = tid & (TK - 1), tgk = tid / TK;
+            for (int i = tgk; i < N; i += GK) {
+                const int e0 = a.omega_ptr[i], e1 = a.omega_ptr[i + 1];
+                for (int r = tr; r < K; r += TK) {
+                    const double xi = X[i * N + r];
+                    double acc = 0.0;
+                    for (int e = e0; e < e1; ++e) acc += xi - X[a.omega_adj[e] * N + r];
+                    Wn[i * K + r] = acc;
+                }
+            }
+        }
+        __syncthreads();
         for (int k = tid; k < K * K; k += nt) {
             const int r = k / K, cidx = k % K;
             double s = 0.0;
-            for (int e = 0; e < a.n_omega_edges; ++e) {
-                const int i = a.omega_i[e], j = a.omega_j[e];
-                s += (X[i * N + r] - X[j * N + r]) * (X[i * N + cidx] - X[j * N + cidx]);
-            }
+            for (int i = 0; i < N; ++i) s = fma(X[i * N + r], Wn[i * K + cidx], s);
             S[r * K + cidx] = 2.0 * s;   // both (i,j) and (j,i) are nonzeros of omega
         }
         __syncthreads();
-        jacobi_eig(S, E, K, K, cs, red);
+        for (int k = tid; k < K * K; k += nt) {
+            const int r = k / K, cidx = k % K;
+            if (r < cidx) {
+                const double m = 0.5 * (S[r * K + cidx] + S[cidx * K + r]);
+                S[r * K + cidx] = m;
+                S[cidx * K + r] = m;
+            }
+        }
+        __syncthreads();
+        BI_TICK("scatter");
+        jacobi_eig(S, E, K, K, cs, pq, red);
+        BI_TICK("eig_proj");
         for (int i = tid; i < K; i += nt) lam[i] = S[i * K + i];
         __syncthreads();
         sort_desc(lam, K, order);
@@ -355,7 +466,7 @@ __global__ void k_bounds_init(const BiArgs a)
     }
 }
 
-size_t small_bytes(int N) { return (size_t)((N + 2) + 34 + N + N + (N + 1) / 2 + 1) * sizeof(double); }
+size_t small_bytes(int N) { return (size_t)gik_bi_small_doubles(N) * sizeof(double); }
 
 int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
 {
@@ -364,6 +475,8 @@ int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
     a.n_goal = p->n_goal;
     a.n_goal_edges = p->n_goal_edges;
     a.n_omega_edges = p->n_omega_edges;
+    a.goal_p = p->n_goal_edges > 0 ? p->goal_p : -1;
+    a.goal_q = p->n_goal_edges > 0 ? p->goal_q : -1;
     a.bs_lower = p->bs_lower;
     a.bs_upper = p->bs_upper;
     a.goal_edge_i = p->goal_edge_i;
@@ -371,9 +484,13 @@ int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
     a.goal_edge_slot = p->goal_edge_slot;
     a.omega_i = p->omega_i;
     a.omega_j = p->omega_j;
+    a.omega_ptr = p->omega_ptr;
+    a.omega_adj = p->omega_adj;
     const size_t mat = (size_t)N * N * sizeof(double);
     size_t smem = small_bytes(N) + (p->bi_mode == 0 ? 3 : (p->bi_mode == 1 ? 2 : 0)) * mat;
-    int threads = N <= 20 ? 32 : (N <= 48 ? 128 : 256);
+    // measured (B200, goals per ms): N = 16: 32 threads 3.9 k, 64: 3.2 k; N = 44: 128: 107, 256: 135; N = 118: 256: 5.8, 512: 7.9
+    int threads = N <= 20 ? 32 : (N <= 48 ? 256 : 512);
+    if (const char *t = getenv("GIK_BI_THREADS")) threads = atoi(t);   // experiments
     int blocks = a.B;
     a.use_scratch = p->bi_mode;
     a.scratch = p->bi_scratch;

@@ -268,6 +268,13 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
             for (int j = i + 1; j < N; ++j)
                 if (d->omega[(size_t)i * N + j]) { oi.push_back(i); oj.push_back(j); }
     p->n_omega_edges = (int)oi.size();
+    std::vector<int32_t> optr(N + 1, 0), oadj;
+    if (d->omega)
+        for (int i = 0; i < N; ++i) {
+            for (int j = 0; j < N; ++j)
+                if (j != i && (d->omega[(size_t)i * N + j] || d->omega[(size_t)j * N + i])) oadj.push_back(j);
+            optr[i + 1] = (int32_t)oadj.size();
+        }
 
     // joint-recovery tables (graph_revolute.py:283-310)
     std::vector<double> Trel, qs0;
@@ -293,7 +300,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     // k_bounds_init works on three N x N fp64 matrices per goal: keep them in shared memory when
     // they fit (227 KB per CTA), else spill the third / all three to an L2-resident scratch
     {
-        const size_t small = (size_t)((N + 2) + 34 + N + N + (N + 1) / 2 + 1) * sizeof(double);
+        const size_t small = (size_t)gik_bi_small_doubles(N) * sizeof(double);
         const size_t mat = (size_t)N * N * sizeof(double);
         const size_t cap = 227 * 1024;
         p->bi_mode = small + 3 * mat <= cap ? 0 : (small + 2 * mat <= cap ? 1 : 2);
@@ -335,6 +342,8 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->goal_edge_slot, d->goal_edge_slot, (size_t)d->n_goal_edges);
     ok = ok && !upload(&p->omega_i, oi.data(), oi.size());
     ok = ok && !upload(&p->omega_j, oj.data(), oj.size());
+    ok = ok && !upload(&p->omega_ptr, optr.data(), optr.size());
+    ok = ok && !upload(&p->omega_adj, oadj.data(), oadj.size());
     if (d->n_joints > 0 && d->T0) {
         ok = ok && !upload(&p->T0, d->T0, (size_t)(d->n_joints + 1) * 16);
         ok = ok && !upload(&p->Trel, Trel.data(), Trel.size());
@@ -350,7 +359,7 @@ extern "C" int gik_plan_destroy(GikPlan *p)
     if (!p) return GIK_OK;
     void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_goal_i, p->dense_goal_j,
                     p->dense_goal_slot, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
-                    p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_i,
+                    p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_ptr, p->omega_adj, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};
     for (void *q : ptrs)
         if (q) cudaFree(q);
