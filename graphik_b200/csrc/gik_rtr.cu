@@ -406,7 +406,7 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
     const char *force = getenv("GIK_RTR_GENERIC");
     if (force && force[0] == '1') kernel = GIK_KERNEL_GENERIC;
     if (kernel == GIK_KERNEL_AUTO) {
-        if (p->N <= 32) kernel = (B >= 16384 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
+        if (p->N <= 32) kernel = (B >= 49152 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
         else kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE
                       : (p->fast2_info ? GIK_KERNEL_LATENCY : GIK_KERNEL_GENERIC);
     }

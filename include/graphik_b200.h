@@ -104,12 +104,15 @@ typedef struct {
 } GikSolveOpts;
 
 /* gik_rtr_solve implementations (identical algorithm, different mapping to the SM) */
-#define GIK_KERNEL_AUTO 0        /* N <= 32: latency kernel, throughput kernel for B >= 16384;
-                                    N > 32: dense kernel when >= 1/8 of the node pairs carry a term, else generic */
-#define GIK_KERNEL_LATENCY 1     /* one warp per problem, register slot cache (N <= 32) */
+#define GIK_KERNEL_AUTO 0        /* N <= 32: latency kernel, throughput kernel for B >= 49152;
+                                    N > 32: dense kernel when >= 1/8 of the node pairs carry a term (and no pair
+                                    carries two), else the two-nodes-per-lane warp kernel (N <= 64), else generic */
+#define GIK_KERNEL_LATENCY 1     /* one warp per problem: register slot cache (N <= 32), two nodes per lane with a
+                                    shared-memory slot cache (32 < N <= 64) */
 #define GIK_KERNEL_THROUGHPUT 2  /* two problems per warp in lock-step (N <= 16) */
 #define GIK_KERNEL_GENERIC 3     /* W-lane groups, any N <= 128 */
-#define GIK_KERNEL_DENSE 4       /* one CTA per problem, dense target matrix in shared memory (32 < N <= 128) */
+#define GIK_KERNEL_DENSE 4       /* one CTA per problem, two CTAs per SM, packed symmetric pair cache in shared
+                                    memory (32 < N <= 128) */
 
 const char *gik_last_error(void);
 int gik_version(void);

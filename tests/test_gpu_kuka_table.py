@@ -63,3 +63,52 @@ def test_kuka_table_pipeline_vs_reference():
         for k in range(K):   # reported cost == lcost of the returned points
             P = orc.Problem(g["D_goal"][k], g["omega"][k], g["psi_L"][k], g["psi_U"][k])
             assert abs(P.cost(x[k]) - f[k]) <= 1e-11 * max(1.0, f[k])
+
+
+def test_kuka_table_intended_obstacle_semantics_vs_oracle():
+    """with obstacle_semantics="intended" every joint point p_i gets a lower-bound (hinge)
+    term against every obstacle sphere (7 x 100 extra LO terms).  Same kernels, checked against the oracle on the
+    same matrices: cost / gradient / Hessian-vector and the leading trust-region decisions.  The 100 pairs
+    (p_n, obstacle) then carry TWO terms (the goal's exact distance and the hinge), which the dense pair cache cannot
+    represent: AUTO must fall back to the generic group kernel and still agree with the oracle."""
+    from graphik_b200.engine import BatchIK, make_opts
+    from oracle import oracle as orc
+    robot, graph = load_kuka_table(graph_params={"obstacle_semantics": "intended"})
+    eng = BatchIK(graph)
+    a = eng.plan._a
+    assert eng.plan.N == 118 and eng.plan.n_terms == 5609 + 9 + 6 + 700
+    rng = np.random.RandomState(7)
+    K = 3
+    Q = -np.pi + 2 * np.pi * rng.rand(K, robot.n)
+    T = robot.fk_all(Q)[:, robot.n]
+    gd = eng.goal_distances(T)
+    Y0 = eng.initialization(gd)
+    gdh, Y0h = gd.cpu().numpy(), Y0.cpu().numpy()
+    gs = a["goal_slot"]
+    ii, jj = np.nonzero(gs >= 0)
+    W = rng.normal(size=Y0h.shape)
+    f, gr = eng.cost_grad(Y0, gd)
+    hv = eng.hessvec(Y0, W, gd).cpu().numpy()
+    out = eng.solve_points(gd, Y0, trace_rows=8, opts=make_opts({"maxiter": 150}))
+    tr = out["trace"].cpu().numpy()
+    x, fx = out["x"].cpu().numpy(), out["f(x)"].cpu().numpy()
+    n_active0 = 0
+    for k in range(K):
+        D = a["D_static"].copy()
+        D[ii, jj] = gdh[k, gs[ii, jj]]
+        P = orc.Problem(D, a["omega_f"], a["psi_L"], a["psi_U"])
+        fo, go, ho = P.cost(Y0h[k]), P.grad(Y0h[k]), P.hess(Y0h[k], W[k])
+        assert abs(float(f[k]) - fo) <= 1e-12 * fo
+        assert np.max(np.abs(gr[k].cpu().numpy() - go)) <= 1e-12 * np.max(np.abs(go))
+        assert np.max(np.abs(hv[k] - ho)) <= 1e-12 * np.max(np.abs(ho))
+        ref = P.solve(Y0h[k], params={"maxiter": 8}, trace_rows=8)["trace"]
+        m = min(len(ref), 4)
+        assert np.array_equal(tr[k, :m][:, [1, 2, 4]], ref[:m][:, [1, 2, 4]]), (k, tr[k, :m], ref[:m])
+        np.testing.assert_allclose(tr[k, :m, 3], ref[:m, 3], rtol=1e-6)
+        assert abs(P.cost(x[k]) - fx[k]) <= 1e-11 * max(1.0, fx[k])
+        # obstacle hinges: squared distance p_i -- o_k below radius^2 at the start?
+        d2 = np.sum((Y0h[k][:, None, :] - Y0h[k][None, :, :]) ** 2, -1)
+        obst = (a["psi_L"] > 0) & (a["omega_f"] == 0)
+        n_active0 += int(np.sum(obst & (d2 < a["psi_L"])))
+    assert np.all(fx < 0.05 * f.cpu().numpy()), (fx, f)
+    print("obstacle hinge terms active at the initial points:", n_active0 // 2)
