@@ -488,8 +488,9 @@ int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
     a.omega_adj = p->omega_adj;
     const size_t mat = (size_t)N * N * sizeof(double);
     size_t smem = small_bytes(N) + (p->bi_mode == 0 ? 3 : (p->bi_mode == 1 ? 2 : 0)) * mat;
-    // measured (B200, goals per ms): N = 16: 32 threads 3.9 k, 64: 3.2 k; N = 44: 128: 107, 256: 135; N = 118: 256: 5.8, 512: 7.9
-    int threads = N <= 20 ? 32 : (N <= 48 ? 256 : 512);
+    // measured on B200: N = 16: 32 threads 3.9 k goals / ms (64 threads: 3.2 k); N = 44, 65 536 goals: 128 threads
+    // 371 ms, 256 threads 479 ms (96 registers: 5 vs 2 CTAs / SM); N = 118 (one CTA / SM): 256 threads 5.8 goals / ms, 512: 7.9
+    int threads = N <= 20 ? 32 : (N <= 64 ? 128 : 512);
     if (const char *t = getenv("GIK_BI_THREADS")) threads = atoi(t);   // experiments
     int blocks = a.B;
     a.use_scratch = p->bi_mode;
