@@ -245,19 +245,51 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     std::vector<double> dense_t;
     std::vector<unsigned char> dense_k;
     std::vector<int32_t> dgi, dgj, dgs;
+    std::vector<unsigned char> hub_k;
+    std::vector<double> hub_t;
+    p->dense_hub = -1;
     if (N > 32 && N <= 128) {
         dense_t.assign((size_t)N * N, 0.0);
         dense_k.assign((size_t)N * N, 3);
+        // A pair may carry a SECOND term (never goal dependent) when all such pairs share one node, the hub:
+        // with obstacle_semantics="intended" the pairs (p_n, obstacle) hold the goal's exact distance and the
+        // obstacle hinge.  The second terms live in a row of per-partner tables (hub_kind / hub_target).
         bool representable = true;
+        int hub_a = -1, hub_b = -1;   // remaining hub candidates
+        hub_k.assign(N, 3);
+        hub_t.assign(N, 0.0);
+        std::vector<int> second_i, second_j, second_t;
         for (int t = 0; t < d->n_terms && representable; ++t) {
             const int i = d->term_i[t], j = d->term_j[t];
-            if (dense_k[(size_t)i * N + j] != 3) { representable = false; break; }   // two terms on one pair
+            const int gs = d->term_goal ? d->term_goal[t] : -1;
+            if (dense_k[(size_t)i * N + j] != 3) {           // second (or later) term on this pair
+                if (gs >= 0) { representable = false; break; }
+                if (hub_a < 0) { hub_a = i; hub_b = j; }
+                else {
+                    const bool a_ok = hub_a == i || hub_a == j, b_ok = hub_b >= 0 && (hub_b == i || hub_b == j);
+                    if (!a_ok && !b_ok) { representable = false; break; }
+                    if (!a_ok) { hub_a = hub_b; }
+                    if (!(a_ok && b_ok)) hub_b = -1;
+                }
+                second_i.push_back(i); second_j.push_back(j); second_t.push_back(t);
+                continue;
+            }
             dense_k[(size_t)i * N + j] = dense_k[(size_t)j * N + i] = (unsigned char)d->term_kind[t];
             dense_t[(size_t)i * N + j] = dense_t[(size_t)j * N + i] = d->term_target[t];
-            const int gs = d->term_goal ? d->term_goal[t] : -1;
             if (gs >= 0) { dgi.push_back(i); dgj.push_back(j); dgs.push_back(gs); }
         }
-        if (!representable) { dense_t.clear(); dense_k.clear(); dgi.clear(); dgj.clear(); dgs.clear(); }
+        p->dense_hub = -1;
+        if (representable && !second_t.empty()) {
+            p->dense_hub = hub_a;
+            for (size_t k = 0; k < second_t.size() && representable; ++k) {
+                const int partner = second_i[k] == hub_a ? second_j[k] : second_i[k];
+                if ((second_i[k] != hub_a && second_j[k] != hub_a) || hub_k[partner] != 3) { representable = false; break; }  // third term
+                hub_k[partner] = (unsigned char)d->term_kind[second_t[k]];
+                hub_t[partner] = d->term_target[second_t[k]];
+            }
+        }
+        if (!representable) { dense_t.clear(); dense_k.clear(); dgi.clear(); dgj.clear(); dgs.clear(); p->dense_hub = -1; }
+        if (p->dense_hub < 0) { hub_k.clear(); hub_t.clear(); }
     }
     p->n_dense_goal = (int)dgi.size();
 
@@ -328,6 +360,8 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->duo_target, dtarget.data(), dtarget.size());
     ok = ok && !upload(&p->dense_target, dense_t.data(), dense_t.size());
     ok = ok && !upload(&p->dense_kind, dense_k.data(), dense_k.size());
+    ok = ok && !upload(&p->dense_hub_kind, hub_k.data(), hub_k.size());
+    ok = ok && !upload(&p->dense_hub_target, hub_t.data(), hub_t.size());
     ok = ok && !upload(&p->dense_goal_i, dgi.data(), dgi.size());
     ok = ok && !upload(&p->dense_goal_j, dgj.data(), dgj.size());
     ok = ok && !upload(&p->dense_goal_slot, dgs.data(), dgs.size());
@@ -357,7 +391,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
 extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
-    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_goal_i, p->dense_goal_j,
+    void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_hub_kind, p->dense_hub_target, p->dense_goal_i, p->dense_goal_j,
                     p->dense_goal_slot, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_ptr, p->omega_adj, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0};

@@ -63,6 +63,9 @@ struct CtaTables {
     const int32_t *goal_i, *goal_j, *goal_slot;
     int n_goal_edges;
     int gp, gq;                 // node indices of p_n, q_n (-1: no goal-dependent targets)
+    int hub;                    // node whose pairs carry a second term (-1: none)
+    const unsigned char *hub_kind;  // [N] kind of the second term of the pair (hub, i), 3 = none
+    const double *hub_target;       // [N]
 };
 
 // butterfly over a warp, lane 0 stores K partial sums
@@ -113,7 +116,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
     double *redF = redB + kOwnWarps * kRedB;            // [kWarps] cost shares of the slices
     double *Tp = redF + kWarps;                         // [NPAD] targets of the pairs (., p_n) for this problem
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
-    double *goal = Tq + NPAD;                           // [n_goal]
+    double *Hc2 = Tq + NPAD;                            // [NPAD] 2 act (d - T) of the second terms around the hub node
+    double *goal = Hc2 + NPAD;                          // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
     const int gp = tb.gp, gq = tb.gq;
     const GikSolveOpts &o = a.o;
@@ -121,10 +125,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
 
     for (int e = tid; e < c2_doubles(N); e += kThreads) C2[e] = 0.0;
     for (int e = tid; e < 3 * NPAD; e += kThreads) { P2[e] = 0.0; V[e] = 0.0; }   // padding nodes stay at 0
+    for (int e = tid; e < NPAD; e += kThreads) Hc2[e] = 0.0;
     __syncthreads();
 
     double xt[NB][3];           // 2 * coordinates of this lane's tile nodes at the cached point
     uint32_t amask[NB];         // bit jj: term (tile node m, neighbour jlo + jj) active there
+    uint32_t hact = 0u;         // bit m: second term of the pair (tile node m, hub) active there (hub's slice only)
+    const int hub = tb.hub;
+    const bool hub_warp = hub >= jlo && hub < jhi;   // this warp's slice contains the hub neighbour
     // c2(i = lane + 32 m, j) in the packed cache is a row entry of block (m, jb) when m <= jb and a column
     // entry of block (jb, m) otherwise; padding lanes of a ragged last block re-read its last row
     int col_off[NB];
@@ -213,7 +221,49 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                 }
             }
         }
+        double react[3] = {0.0, 0.0, 0.0};
+        if (hub_warp) {
+            // second terms of the pairs (i, hub), evaluated from the partner's side only; the hub node gets the
+            // reaction (the term seen from the hub is the mirror image), the cost counts them twice before the 0.5
+            const double px = P2[hub], py = P2[NPAD + hub], pz = P2[2 * NPAD + hub];
+            double fh = 0.0;
+            hact = 0u;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                const int i = lane + 32 * m;
+                const int ic = min(i, N - 1);
+                const unsigned kind = i < N ? tb.hub_kind[i] : 3u;
+                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                const double d4 = dx * dx + dy * dy + dz * dz;
+                double rr = fma(0.25, d4, -tb.hub_target[ic]);
+                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
+                                 ((kind == GIK_TERM_UP) & (rr > 0.0));
+                rr = act ? rr : 0.0;
+                fh = fma(rr, rr, fh);
+                gpart[m][0] = fma(rr, dx, gpart[m][0]);
+                gpart[m][1] = fma(rr, dy, gpart[m][1]);
+                gpart[m][2] = fma(rr, dz, gpart[m][2]);
+                react[0] = fma(rr, dx, react[0]);
+                react[1] = fma(rr, dy, react[1]);
+                react[2] = fma(rr, dz, react[2]);
+                Hc2[i] = 2.0 * rr;
+                hact |= act ? (1u << m) : 0u;
+            }
+            fpart = fma(2.0, fh, fpart);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) react[q] += __shfl_xor_sync(GIK_FULL_MASK, react[q], off, 32);
+            }
+        }
         store_partials(gpart);
+        if (hub_warp) {
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + hub] -= react[q];
+            }
+        }
         double f1[1] = {0.5 * fpart};   // every undirected term is seen from both ends
         warp_sum_store<1>(f1, redF + warp, lane == 0);
     };
@@ -248,7 +298,35 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                 bit <<= 1;
             }
         }
+        double react[3] = {0.0, 0.0, 0.0};
+        if (hub_warp) {
+            const double px = P2[hub], py = P2[NPAD + hub], pz = P2[2 * NPAD + hub];
+            const double vx = V[hub], vy = V[NPAD + hub], vz = V[2 * NPAD + hub];
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                const double c2 = Hc2[lane + 32 * m];
+                const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
+                double s = dx * wx + dy * wy + dz * wz;
+                s = (hact >> m & 1u) ? s : 0.0;
+                const double ax = fma(s, dx, c2 * wx), ay = fma(s, dy, c2 * wy), az = fma(s, dz, c2 * wz);
+                z[m][0] += ax; z[m][1] += ay; z[m][2] += az;
+                react[0] += ax; react[1] += ay; react[2] += az;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) react[q] += __shfl_xor_sync(GIK_FULL_MASK, react[q], off, 32);
+            }
+        }
         store_partials(z);
+        if (hub_warp) {
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + hub] -= react[q];
+            }
+        }
     };
 
     auto total_cost = [&]() -> double {
@@ -485,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
 size_t cta_smem_bytes(int N, int n_goal)
 {
     const int goal_pad = (n_goal + 1) & ~1;
-    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 2) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
+    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 3) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
                       sizeof(double) + 2 * sizeof(int);
     return (smem + 15) & ~(size_t)15;
 }
@@ -522,6 +600,9 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     tb.n_goal_edges = p->n_dense_goal;
     tb.gp = p->n_dense_goal > 0 ? p->goal_p : -1;
     tb.gq = p->n_dense_goal > 0 ? p->goal_q : -1;
+    tb.hub = p->dense_hub;
+    tb.hub_kind = p->dense_hub_kind;
+    tb.hub_target = p->dense_hub_target;
     switch ((N + 31) / 32) {
         case 2: return launch_cta<2>(p, a, tb, smem, st);
         case 3: return launch_cta<3>(p, a, tb, smem, st);

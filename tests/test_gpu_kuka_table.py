@@ -69,8 +69,8 @@ def test_kuka_table_intended_obstacle_semantics_vs_oracle():
     """with obstacle_semantics="intended" every joint point p_i gets a lower-bound (hinge)
     term against every obstacle sphere (7 x 100 extra LO terms).  Same kernels, checked against the oracle on the
     same matrices: cost / gradient / Hessian-vector and the leading trust-region decisions.  The 100 pairs
-    (p_n, obstacle) then carry TWO terms (the goal's exact distance and the hinge), which the dense pair cache cannot
-    represent: AUTO must fall back to the generic group kernel and still agree with the oracle."""
+    (p_n, obstacle) then carry TWO terms (the goal's exact distance and the hinge); the dense kernel keeps the second
+    terms in a per-partner row around the hub node p_n and must agree with the oracle and with the group kernel."""
     from graphik_b200.engine import BatchIK, make_opts
     from oracle import oracle as orc
     robot, graph = load_kuka_table(graph_params={"obstacle_semantics": "intended"})
@@ -89,8 +89,13 @@ def test_kuka_table_intended_obstacle_semantics_vs_oracle():
     W = rng.normal(size=Y0h.shape)
     f, gr = eng.cost_grad(Y0, gd)
     hv = eng.hessvec(Y0, W, gd).cpu().numpy()
-    out = eng.solve_points(gd, Y0, trace_rows=8, opts=make_opts({"maxiter": 150}))
+    out = eng.solve_points(gd, Y0, trace_rows=8, opts=make_opts({"maxiter": 150, "kernel": "dense"}))
+    gen = eng.solve_points(gd, Y0, trace_rows=8, opts=make_opts({"maxiter": 8, "kernel": "generic"}))
     tr = out["trace"].cpu().numpy()
+    tg = gen["trace"].cpu().numpy()
+    assert np.array_equal(tr[:, :4][:, :, [1, 2, 4]], tg[:, :4][:, :, [1, 2, 4]])
+    # a dense launch that silently fell back to the group kernel would reproduce its bits
+    assert not np.array_equal(tr[:, :8, 3], tg[:, :8, 3])
     x, fx = out["x"].cpu().numpy(), out["f(x)"].cpu().numpy()
     n_active0 = 0
     for k in range(K):
