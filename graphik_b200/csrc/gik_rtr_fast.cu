@@ -21,73 +21,13 @@
 #include <cstdlib>
 
 #include "gik_rtr.cuh"
+#include "gik_warp.cuh"
 
 namespace {
 
 constexpr int kThreads = 32;            // one warp = one problem per CTA: a straggler pins only its own warp's
                                         // registers, so the next batch's kernel can move in beside it
 constexpr int kWarps = kThreads / 32;
-
-template <int LPN, int K>
-__device__ __forceinline__ void node_allreduce(double (&v)[K])
-{
-#pragma unroll
-    for (int off = 16; off >= LPN; off >>= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
-    }
-}
-
-// Transposed butterfly all-reduce of KP (4 or 8) scalars over the nodes of a warp.  At each of
-// the first log2(KP) levels a lane keeps half of its values and ships the other half to its
-// partner, so the shuffle count is KP + 2 * (remaining levels) instead of KP * levels; the
-// totals are then fetched from the lanes that own them.  Every lane ends with identical bits.
-// (ncu on the plain butterfly: SHFL issues at ~4 cycles each and was 23 % of all instructions.)
-template <int LPN, int KP>
-__device__ __forceinline__ void node_allreduce_t(double (&v)[KP], int lane)
-{
-    static_assert(KP == 4 || KP == 8, "KP must be 4 or 8");
-    double cur[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) cur[k] = v[k];
-    int cnt = KP;
-#pragma unroll
-    for (int off = 16; off >= LPN; off >>= 1) {
-        if (cnt > 1) {
-            const int half = cnt / 2;
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int k = 0; k < KP / 2; ++k) {
-                if (k < half) {
-                    const double keep = up ? cur[half + k] : cur[k];
-                    const double send = up ? cur[k] : cur[half + k];
-                    cur[k] = keep + __shfl_xor_sync(GIK_FULL_MASK, send, off, 32);
-                }
-            }
-            cnt = half;
-        } else {
-            cur[0] += __shfl_xor_sync(GIK_FULL_MASK, cur[0], off, 32);
-        }
-    }
-    // owner of scalar k: lane bits (16, 8[, 4]) spell k, most significant first
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int src = (KP == 8) ? (((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4)
-                                  : (((k >> 1) & 1) * 16 + (k & 1) * 8);
-        v[k] = __shfl_sync(GIK_FULL_MASK, cur[0], src, 32);
-    }
-}
-
-// sum over the LPN lanes of a node (both lanes end with identical bits)
-template <int LPN, int K>
-__device__ __forceinline__ void pair_combine(double (&v)[K])
-{
-#pragma unroll
-    for (int off = LPN / 2; off > 0; off >>= 1) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], off, 32);
-    }
-}
 
 struct SlotCache {
     double dx, dy, dz;  // 2 * act * (x_i - x_j): zero for an inactive hinge, so (D.w) D = 4 act <d,w> d
@@ -113,7 +53,8 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
     double *V = P + 3 * NPW;
     double *goal = V + 3 * NPW;
     double *tgt = goal + goal_pad + lane;   // [SPL][32] per-problem targets of this warp's slots
-    double *scm = tgt + SPL * 32;           // [SPL][4][32] slot cache when SMC
+    // slot cache when SMC: [SPL][2][32 lanes] double2 {dx, dy}, {dz, c2} -- two conflict-free LDS.128 per slot
+    double2 *scm = reinterpret_cast<double2 *>(goal + goal_pad + SPL * 32) + lane;
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
 
@@ -164,8 +105,8 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
                 gz = fma(rr, dz, gz);
                 const double two = act ? 2.0 : 0.0;
                 if (SMC) {
-                    scm[(s * 4 + 0) * 32] = two * dx; scm[(s * 4 + 1) * 32] = two * dy;
-                    scm[(s * 4 + 2) * 32] = two * dz; scm[(s * 4 + 3) * 32] = 2.0 * rr;
+                    scm[(s * 2 + 0) * 32] = make_double2(two * dx, two * dy);
+                    scm[(s * 2 + 1) * 32] = make_double2(two * dz, 2.0 * rr);
                 } else {
                     sc[s].dx = two * dx; sc[s].dy = two * dy; sc[s].dz = two * dz;
                     sc[s].c2 = 2.0 * rr;
@@ -221,10 +162,13 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
                     for (int s = 0; s < SPL; ++s) {
                         const int jn = GIK_SLOT_NBR(info[s]);
                         const double wx = dl[0] - V[jn], wy = dl[1] - V[NPW + jn], wz = dl[2] - V[2 * NPW + jn];
-                        const double cx = SMC ? scm[(s * 4 + 0) * 32] : sc[s].dx;
-                        const double cy = SMC ? scm[(s * 4 + 1) * 32] : sc[s].dy;
-                        const double cz = SMC ? scm[(s * 4 + 2) * 32] : sc[s].dz;
-                        const double c2 = SMC ? scm[(s * 4 + 3) * 32] : sc[s].c2;
+                        double cx, cy, cz, c2;
+                        if (SMC) {
+                            const double2 a0 = scm[(s * 2 + 0) * 32], a1 = scm[(s * 2 + 1) * 32];
+                            cx = a0.x; cy = a0.y; cz = a1.x; c2 = a1.y;
+                        } else {
+                            cx = sc[s].dx; cy = sc[s].dy; cz = sc[s].dz; c2 = sc[s].c2;
+                        }
                         const double t = fma(cx, wx, fma(cy, wy, cz * wz));
                         z[0] = fma(c2, wx, z[0]);
                         z[1] = fma(c2, wy, z[1]);
@@ -424,7 +368,7 @@ __device__ __forceinline__ void rtr_fast2_body(const RtrArgs &a, const uint32_t 
     double *V = P + 3 * NPW;
     double *goal = V + 3 * NPW;
     double *tgt = goal + goal_pad + lane;   // [ST][32] per-problem targets of this lane's slots
-    double *scm = tgt + ST * 32;            // [ST][4][32] slot cache
+    double2 *scm = reinterpret_cast<double2 *>(goal + goal_pad + ST * 32) + lane;   // [ST][2][32] double2 {dx, dy}, {dz, c2}
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
 
@@ -493,8 +437,8 @@ __device__ __forceinline__ void rtr_fast2_body(const RtrArgs &a, const uint32_t 
                 ga[m][1] = fma(rr, dy, ga[m][1]);
                 ga[m][2] = fma(rr, dz, ga[m][2]);
                 const double two = act ? 2.0 : 0.0;
-                scm[(s * 4 + 0) * 32] = two * dx; scm[(s * 4 + 1) * 32] = two * dy;
-                scm[(s * 4 + 2) * 32] = two * dz; scm[(s * 4 + 3) * 32] = 2.0 * rr;
+                scm[(s * 2 + 0) * 32] = make_double2(two * dx, two * dy);
+                scm[(s * 2 + 1) * 32] = make_double2(two * dz, 2.0 * rr);
             }
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -557,8 +501,8 @@ __device__ __forceinline__ void rtr_fast2_body(const RtrArgs &a, const uint32_t 
                         const int m = s < S0 ? 0 : 1;
                         const int jn = GIK_SLOT_NBR(info[s]);
                         const double wx = dl[m][0] - V[jn], wy = dl[m][1] - V[NPW + jn], wz = dl[m][2] - V[2 * NPW + jn];
-                        const double cx = scm[(s * 4 + 0) * 32], cy = scm[(s * 4 + 1) * 32];
-                        const double cz = scm[(s * 4 + 2) * 32], c2 = scm[(s * 4 + 3) * 32];
+                        const double2 a0 = scm[(s * 2 + 0) * 32], a1 = scm[(s * 2 + 1) * 32];
+                        const double cx = a0.x, cy = a0.y, cz = a1.x, c2 = a1.y;
                         const double t = fma(cx, wx, fma(cy, wy, cz * wz));
                         z[m][0] = fma(c2, wx, z[m][0]);
                         z[m][1] = fma(c2, wy, z[m][1]);
