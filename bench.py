@@ -259,19 +259,12 @@ def main():
         out["q"] = e.joints(out["x"], T)
         return out, ev0, ev1
 
-    # ------------------------------------------------ warm-up = serial steps (one batch at a time);
-    # their device time is reported as `serial` (per-batch latency view of the same workload)
-    serial_ms, serial_rtr_ms = [], []
+    # ------------------------------------------------ warm-up: every slot / stream once (untimed)
     for s in range(n_warm):
         c = s % C
         with torch.cuda.stream(streams[c]):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            _, w0, w1 = device_step(engs[c], T_dev[s])
-            a1.record()
-        a1.synchronize()
-        serial_ms.append(a0.elapsed_time(a1))
-        serial_rtr_ms.append(w0.elapsed_time(w1))
+            device_step(engs[c], T_dev[s])
+        streams[c].synchronize()
     barrier()
 
     # ------------------------------------------------ timed region: K steps, C batches in flight
@@ -363,6 +356,21 @@ def main():
     h2d = B * 16 * 8
     d2h = B * n * 8 + B * 8 + B * 4
 
+    # ------------------------------------------------ serial view: one batch at a time, everything warm.  Reported as
+    # `serial` (latency of a single solve_batch call) and as the trust-region kernel's share of a step, which is
+    # comparable with ncu's serialised launch list
+    serial_ms, serial_rtr_ms = [], []
+    for s in range(min(3, n_warm)):
+        with torch.cuda.stream(streams[0]):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            _, w0, w1 = device_step(engs[0], T_dev[s])
+            a1.record()
+        a1.synchronize()
+        serial_ms.append(a0.elapsed_time(a1))
+        serial_rtr_ms.append(w0.elapsed_time(w1))
+    barrier()
+
     # ------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -375,7 +383,7 @@ def main():
                          "bound smoothing + numpy-eigh initialisation + joint recovery; median outer iters %d"
                          % (args.cpu_sample, int(np.median(res["iterations"])))}
 
-    serial_warm = serial_ms[1:] if len(serial_ms) > 1 else serial_ms
+    serial_warm = serial_ms
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -391,8 +399,8 @@ def main():
                        "parallelism": "goals sharded, dp%d" % world},
             "serial": {"value": world * B / (float(np.mean(serial_warm)) * 1e-3) if serial_warm else None, "unit": UNIT,
                        "ms_per_batch": float(np.mean(serial_warm)) if serial_warm else None,
-                       "note": "one batch at a time (the warm-up steps after the first, which loads the CUDA module): "
-                               "latency of a single solve_batch call, set by the batch's slowest goal (maxiter = 3000)"},
+                       "note": "one batch at a time (3 steps after the timed regions): latency of a single solve_batch "
+                               "call, set by the batch's slowest goal (maxiter = 3000)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_rtr_fast / k_rtr_duo / k_rtr (persistent trust-region solve)",
@@ -409,8 +417,7 @@ def main():
                          # comparable with ncu's serialised launch list (profiles/r1e_launches_bench_steps2.csv: 99.3 %);
                          # with C batches in flight a step's event interval also contains the time its small kernels
                          # wait for SM slots held by the other batches' persistent launches
-                         "kernel_share_of_step": float(np.sum(serial_rtr_ms[1:]) / np.sum(serial_ms[1:]))
-                         if len(serial_ms) > 1 else None,
+                         "kernel_share_of_step": float(np.sum(serial_rtr_ms) / np.sum(serial_ms)) if serial_ms else None,
                          "kernel_share_of_step_concurrent": float(np.sum(rtr_ms) / np.sum(step_ms)),
                          "fp64": {"achieved": alg_flops_total / (local_ms * 1e-3) / 1e12, "peak": fp64_peak_tflops,
                                   "unit": "TFLOP/s", "frac": alg_flops_total / (local_ms * 1e-3) / 1e12 / fp64_peak_tflops,
