@@ -317,13 +317,19 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
     }
 }
 
-// register budget: 168 (12 warps / SM) holds the slot cache of the paired layout without spills;
-// the one-lane-per-node layouts keep it in shared memory and get the same budget
+// Where the slot cache lives and how many warps fit: the paired layout (N <= 16, <= 6 slots per lane) keeps it in
+// registers at 168 registers = 12 warps / SM; one lane per node with <= 9 slots (7-DOF arms: KUKA, LWA4D, Panda)
+// keeps it in registers too, at 238 registers = 8 warps / SM -- measured on KUKA IIWA against the shared-memory cache
+// at 12 warps / SM: same throughput at 65 536 goals (1439 ms), 9 % lower latency at 16 384 (437 vs 480 ms), because the
+// kernel is bound by FP64 / MIO issue and dependent latency, not by resident warps; longer slot lists use shared memory.
+__host__ __device__ constexpr bool fast_cache_in_smem(int LPN, int SPL) { return LPN == 1 ? SPL > 9 : SPL > 6; }
+__host__ __device__ constexpr int fast_min_blocks(int LPN, int SPL) { return (LPN == 1 && SPL <= 9) ? 8 : 12; }
+
 template <int LPN, int SPL>
-__global__ void __launch_bounds__(kThreads, 12) k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info,
-                                                           const double *__restrict__ fast_target)
+__global__ void __launch_bounds__(kThreads, fast_min_blocks(LPN, SPL))
+k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info, const double *__restrict__ fast_target)
 {
-    rtr_fast_body<LPN, SPL, (LPN == 1 || SPL > 6)>(a, fast_info, fast_target);
+    rtr_fast_body<LPN, SPL, fast_cache_in_smem(LPN, SPL)>(a, fast_info, fast_target);
 }
 
 template <int LPN, int SPL>
@@ -331,7 +337,7 @@ int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
     auto kern = k_rtr_fast<LPN, SPL>;
     constexpr int NPW = 32 / LPN;
-    constexpr bool SMC = (LPN == 1 || SPL > 6);
+    constexpr bool SMC = fast_cache_in_smem(LPN, SPL);
     const int goal_pad = (p->n_goal + 1) & ~1;
     const size_t smem = (size_t)kWarps * (6 * NPW + goal_pad + SPL * 32 + (SMC ? SPL * 128 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
