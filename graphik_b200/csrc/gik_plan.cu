@@ -197,7 +197,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
             int &need = k < 32 ? need0 : need1;
             need = deg[order[k]] > need ? deg[order[k]] : need;
         }
-        static const int combos[][2] = {{6, 5}, {8, 5}, {8, 8}, {12, 8}, {12, 12}};
+        static const int combos[][2] = {{6, 5}, {7, 5}, {8, 5}, {8, 8}, {12, 8}, {12, 12}};
         for (const auto &c : combos)
             if (c[0] >= need0 && c[1] >= need1) { p->fast2_S0 = c[0]; p->fast2_S1 = c[1]; break; }
         if (p->fast2_S0) {

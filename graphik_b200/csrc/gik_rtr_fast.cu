@@ -752,6 +752,7 @@ int gik_launch_rtr_fast2(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     if (!p->fast2_info) return 1;
     switch (p->fast2_S0 * 16 + p->fast2_S1) {
         case 6 * 16 + 5: return launch2<6, 5>(p, a, st);
+        case 7 * 16 + 5: return launch2<7, 5>(p, a, st);
         case 8 * 16 + 5: return launch2<8, 5>(p, a, st);
         case 8 * 16 + 8: return launch2<8, 8>(p, a, st);
         case 12 * 16 + 8: return launch2<12, 8>(p, a, st);
