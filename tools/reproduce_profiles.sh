@@ -1,0 +1,31 @@
+#!/bin/bash
+# Commands behind the files in profiles/ (round 1e).  Each block is one `gpurun -- '<command>'` call on a B200 box;
+# outputs land in gpurun_out/ and the summaries were copied to profiles/ by hand (see profiles/README.md).
+set -e
+mkdir -p gpurun_out
+
+# tests + smoke
+python -m pytest tests -m gpu -x -q
+python -c "import __graft_entry__ as g; g.smoke()"
+
+# bench lines (N = 1; N = 2 / 8 under torchrun) and the CPU arm
+python bench.py > gpurun_out/bench_default.json
+python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference.json
+# python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8
+
+# launch list of the bench command (share of each kernel; times are cold-cache and serialised)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null
+
+# per-workload numbers and the batch-size sweep
+python tools/profile_workloads.py ur10:1024 ur10:4096 ur10:16384 ur10:65536 kuka:1024 kuka:4096 kuka:16384 kuka:65536 \
+    lwa4d:4096 chain20:8192 chain20:65536 kuka_table:16384 > gpurun_out/workloads.jsonl
+
+# ncu --set full of the three trust-region kernels (bounded maxiter so that the ~40 replays finish)
+ncu --set full --clock-control none --import-source on -k regex:k_rtr_fast -s 1 -c 1 -o gpurun_out/fast_tp -f \
+    python tools/profile_workloads.py ur10:65536:latency:1:300 > /dev/null
+ncu --set full --clock-control none --import-source on -k regex:k_rtr_fast2 -s 1 -c 1 -o gpurun_out/fast2 -f \
+    python tools/profile_workloads.py chain20:16384:auto:1:60 > /dev/null
+ncu --set full --clock-control none --import-source on -k regex:k_rtr_cta -s 1 -c 1 -o gpurun_out/cta -f \
+    python tools/profile_workloads.py kuka_table:296:dense:1:40 > /dev/null
+# read back with: ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | grep -E 'pipe_fp64|issue_active|dram__bytes|registers'
