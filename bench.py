@@ -162,6 +162,17 @@ def load_workload(name):
     return load_model(name)
 
 
+def baseline_label(robot, batch, world):
+    """Which BASELINE.json config a (robot, per-GPU batch, GPUs) combination is."""
+    if robot == "ur10" and batch == 4096:
+        return ", no obstacles (BASELINE configs[1])"
+    if robot == "kuka_table" and batch * world == 16384:
+        return ", table_environment() obstacles with the reference's semantics (BASELINE configs[2])"
+    if robot == "chain20" and batch * world == 65536:
+        return ", no obstacles (BASELINE configs[3]: 65536 goals sharded over %d GPUs)" % world
+    return ", no obstacles" if robot != "kuka_table" else ", table_environment() obstacles"
+
+
 def run_reference(args):
     """--impl reference: CPU arm.  Rank 0 only; bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -390,8 +401,8 @@ def main():
             "warmup": args.warmup, "warmup_actual": n_warm, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s ProblemGraphRevolute, batch=%d random reachable goal poses per GPU, "
-                                   "no obstacles (BASELINE configs[1])" % (args.robot, B),
+            "config": {"workload": "%s ProblemGraphRevolute, batch=%d random reachable goal poses per GPU%s"
+                                   % (args.robot, B, baseline_label(args.robot, B, world)),
                        "robot": args.robot, "batch_per_gpu": B, "nodes": N, "cost_terms": eng.plan.n_terms,
                        "concurrent_batches": C, "rtr_kernel": args.kernel,
                        "l2": ("flushed between timed steps (256 MiB write)" if C == 1 else
