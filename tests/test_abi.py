@@ -62,3 +62,22 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("oracle/gen_golden.py", ""), \
                     os.path.join(dirpath, f)
+
+
+def test_kernel_selector_names_match_the_header():
+    """engine.make_opts({"kernel": name}) must send the GIK_KERNEL_* value include/graphik_b200.h defines."""
+    from graphik_b200.engine import make_opts
+    header = open(os.path.join(ROOT, "include", "graphik_b200.h")).read()
+    defines = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define GIK_KERNEL_([A-Z]+)\s+(\d+)", header)}
+    assert set(defines) == {"auto", "latency", "throughput", "generic", "dense"}
+    for name, value in defines.items():
+        assert make_opts({"kernel": name}).kernel == value, name
+    with pytest.raises(KeyError):
+        make_opts({"kernel": "no-such-kernel"})
+
+
+def test_every_cuda_source_is_in_the_build_list():
+    """A .cu file that is not in _lib.SOURCES would silently stay out of libgraphik_b200.so."""
+    from graphik_b200 import _lib
+    on_disk = sorted(f for f in os.listdir(_lib.CSRC) if f.endswith(".cu"))
+    assert on_disk == sorted(_lib.SOURCES)
