@@ -23,9 +23,17 @@ def main():
     ap.add_argument("--seed", type=int, default=123)
     args = ap.parse_args()
     load_reference()
-    from gen_golden import _loaders, solve_traced
+    from gen_golden import _loaders, random_dh_chain, solve_traced
     for name in args.robots:
-        robot, graph = _loaders()[name]()
+        if name == "kuka_table":      # BASELINE config 3 as the reference runs it (~25 s per goal)
+            from graphik.utils.utils import table_environment
+            robot, graph = _loaders()["kuka"]()
+            for idx, obs in enumerate(table_environment()):
+                graph.add_spherical_obstacle(f"o{idx}", obs[0], obs[1])
+        elif name.startswith("chain"):  # BASELINE config 4's robot: the same random-DH chain as tests/golden/chain20_*
+            robot, graph, _ = random_dh_chain(int(name[5:]), 0)
+        else:
+            robot, graph = _loaders()[name]()
         n = robot.n
         np.random.seed(args.seed)
         keys = ("T_goal", "Y_init", "Y_sol", "q_sol", "f", "gradnorm", "iterations", "pose_err")
