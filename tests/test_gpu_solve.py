@@ -216,9 +216,9 @@ def test_throughput_kernel_statistics_and_independence():
     assert np.array_equal(o["x"][1].cpu().numpy(), thr["x"][1].cpu().numpy())
 
 
-@pytest.mark.parametrize("name", ["ur10", "kuka"])
+@pytest.mark.parametrize("name", ["ur10", "kuka", "lwa4d", "lwa4p", "panda"])
 def test_end_state_vs_reference_sample(name):
-    """64 goals solved by the UNMODIFIED reference (tests/golden/<robot>_stats.npz, made by
+    """64 (UR10, KUKA) / 48 (LWA4D, LWA4P, Panda) goals solved by the UNMODIFIED reference (tests/golden/<robot>_stats.npz, made by
     oracle/gen_golden_stats.py) against the GPU started from the reference's own Y_init:
     recovered joint angles (same IK branch, 1e-3 rad -- both solvers stop at |g| < 5e-10 but follow
     rounding-perturbed trajectories, so a minority of goals ends in another of the <= 16 IK branches),
