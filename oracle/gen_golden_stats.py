@@ -25,11 +25,19 @@ def main():
     load_reference()
     from gen_golden import _loaders, random_dh_chain, solve_traced
     for name in args.robots:
-        if name == "kuka_table":      # BASELINE config 3 as the reference runs it (~25 s per goal)
+        if name in ("kuka_table", "kuka_table_intended"):      # BASELINE config 3 (~25 s per goal)
             from graphik.utils.utils import table_environment
             robot, graph = _loaders()["kuka"]()
             for idx, obs in enumerate(table_environment()):
                 graph.add_spherical_obstacle(f"o{idx}", obs[0], obs[1])
+                if name == "kuka_table_intended":
+                    # what add_spherical_obstacle (graph_base.py:201-211) means to do and never does on revolute graphs
+                    # (SURVEY App. C.1): the reference's own statements, applied by hand to the joint points p_1..p_n
+                    for i in range(1, robot.n + 1):
+                        graph.add_edge(f"p{i}", f"o{idx}")
+                        graph[f"p{i}"][f"o{idx}"]["bounded"] = ["below"]
+                        graph[f"p{i}"][f"o{idx}"]["lower_limit"] = obs[1]
+                        graph[f"p{i}"][f"o{idx}"]["upper_limit"] = 100
         elif name.startswith("chain"):  # BASELINE config 4's robot: the same random-DH chain as tests/golden/chain20_*
             robot, graph, _ = random_dh_chain(int(name[5:]), 0)
         else:

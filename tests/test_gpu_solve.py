@@ -261,20 +261,24 @@ def test_end_state_vs_reference_sample(name):
         assert np.max(np.abs(Dg - Dr)) < (1e-3 if robot.n == 6 else 5e-2)
 
 
-@pytest.mark.parametrize("name", ["chain20", "kuka_table"])
+@pytest.mark.parametrize("name", ["chain20", "kuka_table", "kuka_table_intended"])
 def test_end_state_vs_reference_sample_redundant_and_dense(name):
     """BASELINE configs 3 and 4 against the UNMODIFIED reference (tests/golden/<name>_stats.npz from
     oracle/gen_golden_stats.py: 32 goals of the 20-DOF chain, 6 of KUKA + table), GPU started from the reference's own
     Y_init.  Redundant arms have a continuum of solutions per pose and rounding-perturbed trajectories end at different
     points of it, so what is compared is what the reference's stopping rule pins: the EDM residual, convergence, and the
-    outer-iteration counts (the CPU oracle differs from the reference by the same amounts)."""
+    outer-iteration counts (the CPU oracle differs from the reference by the same amounts).
+    "kuka_table_intended": the reference run with the obstacle edges add_spherical_obstacle means to add applied to its
+    graph by hand (oracle/gen_golden_stats.py) against obstacle_semantics="intended" here -- one of the
+    six goals ends with an active obstacle hinge (f = 9.26e-5), which the GPU must reproduce."""
     import os
     from helpers import GOLDEN, load_kuka_table
     from graphik_b200.engine import BatchIK
     if not os.path.exists(os.path.join(GOLDEN, name + "_stats.npz")):
         pytest.skip("reference sample not generated")
-    if name == "kuka_table":
-        robot, graph = load_kuka_table()
+    if name.startswith("kuka_table"):
+        robot, graph = load_kuka_table(graph_params={"obstacle_semantics": "intended" if name.endswith("intended")
+                                                     else "reference"})
         eng = BatchIK(graph)
     else:
         robot, graph, eng = _engine(name)
@@ -284,13 +288,14 @@ def test_end_state_vs_reference_sample_redundant_and_dense(name):
     f, it, st = out["f(x)"].cpu().numpy(), out["iterations"].cpu().numpy(), out["status"].cpu().numpy()
     ref_it = g["iterations"]
     print(name, "iterations gpu", it.tolist(), "reference", ref_it.tolist(), "max f gpu %.2e ref %.2e" % (f.max(), g["f"].max()))
-    assert np.all(g["f"] < 1e-12)                      # the reference converged on every goal of the sample
-    assert np.mean((st == 0) & (f < 1e-9)) >= 0.8      # (a perturbed trajectory may stall where the reference did not)
+    # same end cost as the reference: ~0 where it converged to a realisation, the same local minimum where a hinge stays
+    # active (a perturbed trajectory may stall where the reference did not, hence rates)
+    assert np.mean((st == 0) & (np.abs(f - g["f"]) <= np.maximum(1e-9, 1e-3 * g["f"]))) >= 0.8
     assert np.median(f) < 1e-13
     r = np.median(it) / np.median(ref_it)
     assert 0.6 < r < 1.6, r
     assert np.median(np.abs(it - ref_it) / ref_it) < 0.3
-    if name == "kuka_table":
+    if name.startswith("kuka_table"):
         q = eng.joints(out["x"], T).cpu().numpy()
         dq = np.max(np.abs(np.mod(q - g["q_sol"] + np.pi, 2 * np.pi) - np.pi), axis=1)
         print("joint-angle distance to the reference's solution:", np.round(dq, 4).tolist())
