@@ -1,17 +1,18 @@
 #!/usr/bin/env python
 """Headline benchmark: IK solves/sec on batches of random reachable goal poses.
 
-Workload (BASELINE.json configs[1]): UR10 ProblemGraphRevolute, batch = 4096 random goal
-poses per GPU, no obstacles.  One "step" = one pass of the hot path over one batch:
+Workload (BASELINE.json configs[1]): UR10 ProblemGraphRevolute, batch = 4096 random goal poses per GPU,
+no obstacles.  One "step" = one pass of the hot path over one batch:
 T_goal[B,4,4] resident in HBM -> q[B,n], status[B], f[B] resident in HBM
 (goal distances, bound smoothing + initialisation, trust-region solve, joint recovery).
 
-  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
-  python bench.py --impl reference ...                     CPU arm: the oracle port of the
-        reference's algorithm on all host cores (the reference itself is Python and cannot
-        travel to the GPU box; kind = "port")
+  python bench.py --gpus N --steps K --warmup W      this repo's CUDA path, through the public API only:
+        RiemannianSolver.stream() (graphik_b200/pipeline.py) -- K submit() calls, one drain()
+  python bench.py --impl reference ...               CPU arm on the box's host cores: the UNMODIFIED reference
+        (oracle/_ref/reference, one pinned process per core; kind = "reference") or, where no copy of the
+        reference exists, the oracle's C restatement (kind = "port")
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+Prints ONE JSON line (rank 0).  DESIGN.md section "Measurement" explains every field.
 """
 import argparse
 import json
@@ -28,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ik_solves_per_sec"
 UNIT = "solves/s"
+FP64_PEAK_TFLOPS = 34.2     # FP64 FMA peak measured on this pool's B200 with tools/fp64_peak.cu (profiles/r1d_fp64_peak_b200.txt)
 
 
 def goals_for(robot, B, seed):
@@ -41,7 +43,7 @@ def goals_for(robot, B, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING a timed region (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -51,14 +53,16 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        self.rows = []
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -107,48 +111,6 @@ def ncu_traffic(workload):
     return None
 
 
-def oracle_inputs(eng_arrays, goal_d2, Y0):
-    """Per-goal D_goal matrices for the CPU port from the plan's static arrays + goal rows."""
-    a = eng_arrays
-    B = goal_d2.shape[0]
-    D = np.repeat(a["D_static"][None], B, 0)
-    gs = a["goal_slot"]
-    ii, jj = np.nonzero(gs >= 0)
-    D[:, ii, jj] = goal_d2[:, gs[ii, jj]]
-    return D
-
-
-def cpu_port_solve(robot, graph, T, threads):
-    """The reference algorithm restated on the CPU (oracle/): per goal from_pose distances,
-    bound smoothing, initialisation (numpy eigh), trust-region solve (C, OpenMP over goals),
-    joint recovery.  Returns (elapsed seconds, results)."""
-    from graphik_b200.plan import Plan
-    from oracle import oracle as orc
-    a = Plan.arrays_from_graph(graph)
-    B = T.shape[0]
-    anchors = a["anchor_pos"]
-    t0 = time.perf_counter()
-    pq = np.stack([T[:, :3, 3], T[:, :3, 3] + graph.axis_length * T[:, :3, 2]], 1)       # [B,2,3]
-    d = np.linalg.norm(pq[:, :, None, :] - anchors[None, None], axis=-1)                  # [B,2,A]
-    goal_d2 = (d ** 2).reshape(B, -1)
-    D = oracle_inputs(a, goal_d2, None)
-    lower = np.where(np.isnan(graph.lower), 0.0, graph.lower)
-    upper = np.where(np.isnan(graph.upper), np.inf, graph.upper)
-    edge = graph.edge.copy()
-    gs = a["goal_slot"]
-    ii, jj = np.nonzero(gs >= 0)
-    edge[ii, jj] = True
-    Y0 = np.empty((B, graph.number_of_nodes(), 3))
-    for b in range(B):
-        lo, up = lower.copy(), upper.copy()
-        lo[ii, jj] = up[ii, jj] = np.sqrt(goal_d2[b, gs[ii, jj]])
-        lb, ub = orc.bound_smoothing(edge, lo, up)
-        Y0[b] = orc.generate_initialization(lb, ub, a["omega_f"])
-    res = orc.solve_batch(D, a["omega_f"], a["psi_L"], a["psi_U"], Y0, threads=threads)
-    res["q"] = graph.joint_variables_batch(res["x"], T)
-    return time.perf_counter() - t0, res
-
-
 def load_workload(name):
     """Robot + graph of a named workload; "kuka_table" = KUKA IIWA + table_environment() obstacles
     with the reference's (anchor-only) obstacle semantics (BASELINE configs[2])."""
@@ -173,21 +135,112 @@ def baseline_label(robot, batch, world):
     return ", no obstacles" if robot != "kuka_table" else ", table_environment() obstacles"
 
 
+# ---------------------------------------------------------------------------------------------------
+# CPU arms (oracle/ is measurement infrastructure: only this leg of bench.py executes it)
+
+class CpuPort:
+    """The reference algorithm restated on the CPU (oracle/): per goal from_pose distances, bound smoothing (C),
+    initialisation (numpy eigh) -- both spread over worker processes --, trust-region solves (C, OpenMP over goals),
+    joint recovery.  All host cores."""
+
+    kind = "port"
+
+    def __init__(self, robot, graph):
+        from graphik_b200.plan import Plan
+        from oracle import ref_arm
+        self.robot, self.graph = robot, graph
+        self.a = Plan.arrays_from_graph(graph)
+        self.cores = len(ref_arm.usable_cores())
+        self.cpu = ref_arm.cpu_model()
+        self.pool = ref_arm.PortPool(self.cores)
+        a, g = self.a, graph
+        self.lower = np.where(np.isnan(g.lower), 0.0, g.lower)
+        self.upper = np.where(np.isnan(g.upper), np.inf, g.upper)
+        gs = a["goal_slot"]
+        self.ii, self.jj = np.nonzero(gs >= 0)
+        self.slots = gs[self.ii, self.jj]
+        self.edge = g.edge.copy()
+        self.edge[self.ii, self.jj] = True
+
+    def solve(self, T):
+        from oracle import oracle as orc
+        a, graph = self.a, self.graph
+        B = T.shape[0]
+        t0 = time.perf_counter()
+        pq = np.stack([T[:, :3, 3], T[:, :3, 3] + graph.axis_length * T[:, :3, 2]], 1)       # [B,2,3]
+        d = np.linalg.norm(pq[:, :, None, :] - a["anchor_pos"][None, None], axis=-1)          # [B,2,A]
+        goal_d2 = (d ** 2).reshape(B, -1)
+        D = np.repeat(a["D_static"][None], B, 0)
+        D[:, self.ii, self.jj] = goal_d2[:, self.slots]
+        Y0 = self.pool.init_points(self.edge, self.lower, self.upper, self.ii, self.jj, self.slots, goal_d2,
+                                   a["omega_f"])
+        res = orc.solve_batch(D, a["omega_f"], a["psi_L"], a["psi_U"], Y0, threads=self.cores)
+        res["q"] = graph.joint_variables_batch(res["x"], T)
+        return time.perf_counter() - t0, res
+
+    def describe(self, sample, steps):
+        return ("%d goals/step x %d steps; oracle C port of TrustRegions + tCG (OpenMP over goals, %d threads set from "
+                "C), bound smoothing (C) + numpy-eigh initialisation on %d worker processes, joint recovery; %s"
+                % (sample, steps, self.cores, self.cores, self.cpu))
+
+    def close(self):
+        self.pool.close()
+
+
+class CpuReference:
+    """The unmodified reference through its public API, solve_with_riemannian(graph, T_goal, use_jit=True)
+    (riemannian_solver.py:220-234), one pinned process per host core."""
+
+    kind = "reference"
+
+    def __init__(self, workload):
+        from oracle import ref_arm
+        self.pool = ref_arm.ReferencePool(workload)
+        self.cores = len(self.pool.cores)
+        self.cpu = ref_arm.cpu_model()
+
+    def solve(self, T):
+        dt, errs, ok = self.pool.solve(T)
+        return dt, {"pos_err": np.asarray(errs), "ok": np.asarray(ok)}
+
+    def describe(self, sample, steps):
+        return ("%d goals/step x %d steps; UNMODIFIED reference solve_with_riemannian(use_jit=True) incl. from_pose, "
+                "bound_smoothing, joint_variables; one pinned process per core (%d), numba costgrd AOT-built on this "
+                "host, first solve of every process and step discarded; third-party pymanopt/liegroups/urdfpy through "
+                "the stand-ins of oracle/shims; %s" % (sample, steps, self.cores, self.cpu))
+
+    def close(self):
+        self.pool.close()
+
+
+def make_cpu_arm(kind, workload, robot, graph):
+    from oracle import ref_arm
+    if kind in ("auto", "reference") and ref_arm.reference_root() is not None:
+        try:
+            return CpuReference(workload)
+        except Exception as e:   # e.g. numba missing on this host
+            if kind == "reference":
+                raise
+            print("note: reference arm unavailable (%s); using the port" % e, file=sys.stderr)
+    return CpuPort(robot, graph)
+
+
 def run_reference(args):
-    """--impl reference: CPU arm.  Rank 0 only; bounded sample per step."""
+    """--impl reference: CPU arm.  Rank 0 only; every step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     robot, graph = load_workload(args.robot)
-    cores = os.cpu_count() or 1
-    sample = args.cpu_sample
-    times, n_done = [], 0
+    arm = make_cpu_arm(args.cpu_kind, args.robot, robot, graph)
+    sample = args.cpu_sample or (6 * arm.cores if arm.kind == "reference" else 1024)
+    times, n_done, errs = [], 0, []
     for s in range(args.warmup + args.steps):
         _, T = goals_for(robot, sample, seed=1000 + s)
-        dt, res = cpu_port_solve(robot, graph, T, cores)
+        dt, res = arm.solve(T)
         if s >= args.warmup:
             times.append(dt)
             n_done += sample
+    arm.close()
     total = float(np.sum(times))
     value = n_done / total
     line = {
@@ -195,31 +248,53 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s ProblemGraphRevolute, %d random reachable goal poses per step (bounded "
-                               "sample of the batch=%d workload), no obstacles" % (args.robot, sample, args.batch),
+                               "sample of the batch=%d workload)%s" % (args.robot, sample, args.batch,
+                                                                       baseline_label(args.robot, args.batch, 1)),
                    "robot": args.robot, "batch": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d goals/step x %d steps; oracle C port of TrustRegions+tCG with OpenMP over "
-                                   "goals, numpy eigh initialisation, C bound smoothing" % (sample, args.steps)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                         "sample": arm.describe(sample, args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------
+
+def measure_stream(solver, T_list, slots, budget, to_host, record_events=False):
+    """K batches through RiemannianSolver.stream(): submit all, drain, wall time on the host between two device
+    synchronisations.  Returns (seconds, tickets, stream)."""
+    import torch
+    st = solver.stream(slots=slots, inner_budget=budget, to_host=to_host, record_events=record_events)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tickets = [st.submit(T) for T in T_list]
+    st.drain()
+    if to_host:
+        for tk in tickets:
+            tk.ready.synchronize()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, tickets, st
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--robot", default="ur10")
     ap.add_argument("--batch", type=int, default=4096, help="goal poses per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="goals per step of the CPU arm / cpu_baseline")
-    ap.add_argument("--concurrent", type=int, default=8,
-                    help="batches in flight (CUDA streams); 1 = strictly one batch at a time")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: goal poses per step over ALL GPUs (overrides --batch)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="goals per step of the CPU arm (0: chosen per kind)")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"])
+    ap.add_argument("--slots", type=int, default=2, help="IKStream slots (CUDA streams with a carry queue each)")
+    ap.add_argument("--inner-budget", type=int, default=0, help="tCG iterations per goal and launch (0: default)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "latency", "throughput", "generic", "dense"],
                     help="gik_rtr_solve implementation (same results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs / batch-size sweep")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -228,8 +303,7 @@ def main():
     import torch
     import torch.distributed as dist
     from graphik_b200.distributed import gather_stats, summary_stats
-    from graphik_b200.engine import BatchIK
-    from graphik_b200.utils.roboturdf import load_model
+    from graphik_b200.solvers.riemannian_solver import RiemannianSolver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,218 +312,250 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    strong = args.global_batch > 0
+    if strong:
+        args.batch = args.global_batch // world
 
     robot, graph = load_workload(args.robot)
-    C = max(1, args.concurrent)              # batches in flight (one CUDA stream + work counter each)
-    eng = BatchIK(graph, params={"kernel": args.kernel}, device=dev)
-    engs = [eng] + [BatchIK(plan=eng.plan, params={"kernel": args.kernel}, device=dev) for _ in range(C - 1)]   # one work counter per slot
-    streams = [torch.cuda.Stream(device=dev) for _ in range(C)]
-    B, N, n = args.batch, graph.number_of_nodes(), robot.n
-    n_warm = max(args.warmup, C)             # every slot/stream is warmed at least once (untimed)
-    total_steps = n_warm + args.steps
+    solver = RiemannianSolver(graph, {"kernel": args.kernel})
+    eng = solver.engine
+    budget = args.inner_budget or None
+    B, N, n, K = args.batch, graph.number_of_nodes(), robot.n, args.steps
+    n_warm = max(args.warmup, 3)
+    total_steps = n_warm + K
     # a different goal set per step and per rank; all resident in HBM before the timed region
     T_host = [goals_for(robot, B, seed=1000 + s + 7919 * rank)[1] for s in range(total_steps)]
     T_dev = [torch.as_tensor(T, device=dev).contiguous() for T in T_host]
     T_pinned = [torch.as_tensor(T).pin_memory() for T in T_host]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(e, T):
-        """One pass of the hot path with inputs resident in HBM (4 kernels + 1 memset)."""
-        g2 = e.goal_distances(T)
-        Y0 = e.initialization(g2)
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        out = e.solve_points(g2, Y0)
-        ev1.record()
-        out["q"] = e.joints(out["x"], T)
-        return out, ev0, ev1
-
-    # ------------------------------------------------ warm-up: every slot / stream once (untimed)
-    for s in range(n_warm):
-        c = s % C
-        with torch.cuda.stream(streams[c]):
-            device_step(engs[c], T_dev[s])
-        streams[c].synchronize()
+    # ------------------------------------------------ warm-up (untimed): both variants of the stream
+    measure_stream(solver, T_dev[:n_warm], args.slots, budget, False)
+    measure_stream(solver, T_pinned[:n_warm], args.slots, budget, True)
     barrier()
 
-    # ------------------------------------------------ timed region: K steps, C batches in flight
+    # ------------------------------------------------ timed region: K steps, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = sum(e.launches for e in engs)
+    launches0 = eng.launches
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    outs, ev_rtr, ev_step = [], [], []
     t_begin.record()
-    for st in streams:
-        st.wait_event(t_begin)
-    for s in range(args.steps):
-        c = s % C
-        with torch.cuda.stream(streams[c]):
-            flush.zero_() if C == 1 else None      # L2 flush between serial steps; with C > 1 the
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()                              # concurrent batches evict each other's lines
-            out, k0, k1 = device_step(engs[c], T_dev[n_warm + s])
-            e1.record()
-        outs.append(out)
-        ev_rtr.append((k0, k1))
-        ev_step.append((e0, e1))
-    for st in streams:
-        torch.cuda.current_stream(dev).wait_stream(st)
+    _, tickets, st = measure_stream(solver, T_dev[n_warm:], args.slots, budget, False, record_events=True)
     t_end.record()
     barrier()
-    launches = sum(e.launches for e in engs) - launches0
+    launches = eng.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev_step]
-    rtr_ms = [a.elapsed_time(b) for a, b in ev_rtr]
     local_ms = float(t_begin.elapsed_time(t_end))
     t = torch.tensor([local_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * B * args.steps / (total_ms * 1e-3)
+    value = world * B * K / (total_ms * 1e-3)
+    outs = [st.result(tk) for tk in tickets]
+    rtr_ms = [a.elapsed_time(b) for a, b in st.launch_events]
+    stream_stats = st.stats()
 
     # summary statistics: the path's single collective (all-gather of a fixed-size vector)
     agg = {k: torch.cat([o[k] for o in outs]) for k in ("iterations", "status", "f(x)", "n_inner")}
     per_rank, stats = gather_stats(summary_stats(agg, local_ms))
 
+    # sharding exactness: every rank re-solves the head of rank 0's first timed batch; one more all-gather
+    shard_ok = None
+    if world > 1:
+        head = min(256, B)
+        T0 = torch.as_tensor(goals_for(robot, B, seed=1000 + n_warm)[1][:head], device=dev)
+        mine = solver.solve_batch(T0, check=False)["x"].contiguous()
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        shard_ok = bool(all(torch.equal(everyone[0], e) for e in everyone))
+        if rank == 0:
+            shard_ok = shard_ok and bool(torch.equal(outs[0]["x"][:head], everyone[0]))
+
     # roofline of the dominant kernel (k_rtr*): algorithmic bytes of the streaming formulation
     it_sum = float(agg["iterations"].sum())
     in_sum = float(agg["n_inner"].sum())
     alg_bytes_total = 72.0 * N * it_sum + 240.0 * N * in_sum
-    alg_bytes_per_launch = alg_bytes_total / args.steps
-    rtr_avg_ms = float(np.mean(rtr_ms))
+    n_launch = max(len(rtr_ms), 1)
+    alg_bytes_per_launch = alg_bytes_total / n_launch
+    rtr_avg_ms = float(np.mean(rtr_ms)) if rtr_ms else float("nan")
     achieved = alg_bytes_per_launch / (rtr_avg_ms * 1e-3) / 1e9
     aggregate = alg_bytes_total / (local_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
     workload = "%s_b%d" % (args.robot, B)
-    # secondary bound (SURVEY 8d): algorithmic fp64 flops per tCG iteration = 38 per cost term + 60 N + 60,
-    # against the FP64 FMA peak measured on this pool's B200 with tools/fp64_peak.cu (profiles/r1d_fp64_peak_b200.txt)
     alg_flops_total = in_sum * (38.0 * eng.plan.n_terms + 60.0 * N + 60.0)
-    fp64_peak_tflops = 34.2
 
-    # ------------------------------------------------ end to end through the public API (host buffers)
-    from graphik_b200.solvers.riemannian_solver import RiemannianSolver
-    solvers = []
-    for e in engs:
-        sv = RiemannianSolver(graph, {"kernel": args.kernel})
-        sv._engine = e
-        solvers.append(sv)
-    h_out = [(torch.empty((B, n), dtype=torch.float64).pin_memory(), torch.empty((B,), dtype=torch.float64).pin_memory(),
-              torch.empty((B,), dtype=torch.int32).pin_memory()) for _ in range(C)]
-
-    def e2e_step(s, c):
-        streams[c].synchronize()                     # the consumer has taken slot c's previous result
-        with torch.cuda.stream(streams[c]):
-            Tg = T_pinned[s].to(dev, non_blocking=True)
-            o = solvers[c].solve_batch(Tg, check=False)
-            h_out[c][0].copy_(o["q"], non_blocking=True)
-            h_out[c][1].copy_(o["f(x)"], non_blocking=True)
-            h_out[c][2].copy_(o["status"], non_blocking=True)
-
-    for s in range(C):
-        e2e_step(s, s % C)
+    # ------------------------------------------------ end to end through the same public API with HOST buffers
     barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        e2e_step(n_warm + s, s % C)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s, e2e_tickets, e2e_st = measure_stream(solver, T_pinned[n_warm:], args.slots, budget, True)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
+    e2e_value = world * B * K / float(t.item())
     h2d = B * 16 * 8
     d2h = B * n * 8 + B * 8 + B * 4
+    e2e_same = bool(all(np.array_equal(e2e_st.result(a, host=True)["status"].numpy(), o["status"].cpu().numpy())
+                        for a, o in zip(e2e_tickets[:2], outs[:2])))
 
-    # ------------------------------------------------ serial view: one batch at a time, everything warm.  Reported as
-    # `serial` (latency of a single solve_batch call) and as the trust-region kernel's share of a step, which is
-    # comparable with ncu's serialised launch list
-    serial_ms, serial_rtr_ms = [], []
-    for s in range(min(3, n_warm)):
-        with torch.cuda.stream(streams[0]):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            _, w0, w1 = device_step(engs[0], T_dev[s])
-            a1.record()
-        a1.synchronize()
-        serial_ms.append(a0.elapsed_time(a1))
-        serial_rtr_ms.append(w0.elapsed_time(w1))
+    # ------------------------------------------------ one batch at a time through solve_batch (synchronous call)
+    serial_ms = []
+    for s in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        solver.solve_batch(T_dev[s], check=False)
+        torch.cuda.synchronize()
+        serial_ms.append(1e3 * (time.perf_counter() - t0))
+    # ... and one batch at a time through a one-slot stream (deferred stragglers, no overlap between batches)
+    one_s, _, _ = measure_stream(solver, T_dev[n_warm:n_warm + min(K, 16)], 1, budget, False)
+    one_value = world * B * min(K, 16) / one_s
     barrier()
 
-    # ------------------------------------------------ CPU baseline (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        _, Tc = goals_for(robot, args.cpu_sample, seed=1000 + n_warm)
-        cpu_port_solve(robot, graph, Tc[:16], cores)       # warm the OpenMP pool / page in numpy
-        dt, res = cpu_port_solve(robot, graph, Tc, cores)
-        cpu = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "first %d goals of the first timed batch; oracle C port (OpenMP over goals) incl. "
-                         "bound smoothing + numpy-eigh initialisation + joint recovery; median outer iters %d"
-                         % (args.cpu_sample, int(np.median(res["iterations"])))}
+    # ------------------------------------------------ other BASELINE configs + batch-size sweep (N = 1 only)
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = measure_configs(args, dev)
 
-    serial_warm = serial_ms
+    # ------------------------------------------------ CPU baselines (rank 0, N = 1 only)
+    cpu, cpu_ref = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, cpu_ref = cpu_baselines(args, robot, graph, n_warm)
+
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "warmup_actual": n_warm, "ms_per_step": total_ms / args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "warmup_actual": n_warm, "ms_per_step": total_ms / K,
             "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s ProblemGraphRevolute, batch=%d random reachable goal poses per GPU%s"
                                    % (args.robot, B, baseline_label(args.robot, B, world)),
                        "robot": args.robot, "batch_per_gpu": B, "nodes": N, "cost_terms": eng.plan.n_terms,
-                       "concurrent_batches": C, "rtr_kernel": args.kernel,
-                       "l2": ("flushed between timed steps (256 MiB write)" if C == 1 else
-                              "not flushed: %d batches in flight on separate streams evict each other" % C),
+                       "api": "RiemannianSolver.stream(): K submit() calls + drain()",
+                       "stream_slots": args.slots, "inner_budget": stream_stats["inner_budget"],
+                       "rtr_kernel": args.kernel,
+                       "l2": "not flushed: every step reads its own goal set (%d steps x %.1f MB of inputs, outputs and "
+                             "parked states) and batches on different slots evict each other" %
+                             (K, B * (16 + 2 * 3 * N + n + 4) * 8 / 1e6),
                        "parallelism": "goals sharded, dp%d" % world},
-            "serial": {"value": world * B / (float(np.mean(serial_warm)) * 1e-3) if serial_warm else None, "unit": UNIT,
-                       "ms_per_batch": float(np.mean(serial_warm)) if serial_warm else None,
-                       "note": "one batch at a time (3 steps after the timed regions): latency of a single solve_batch "
-                               "call, set by the batch's slowest goal (maxiter = 3000)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "serial": {"value": world * B / (float(np.mean(serial_ms)) * 1e-3), "unit": UNIT,
+                       "ms_per_batch": float(np.mean(serial_ms)),
+                       "note": "one synchronous RiemannianSolver.solve_batch call at a time: its latency is the "
+                               "slowest goal of the batch (maxiter = 3000: ~230 k tCG iterations at the ~0.6 us a lone "
+                               "warp needs per iteration), which no scheduling can shorten without changing results"},
+            "serial_deferred": {"value": one_value, "unit": UNIT, "slots": 1,
+                                "note": "one batch at a time through a ONE-slot stream: goals over the iteration budget "
+                                        "finish in the shadow of the following batches, one drain at the end"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "same_results_as_device_run": e2e_same},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_rtr_fast / k_rtr_duo / k_rtr (persistent trust-region solve)",
-                         # C launches overlap on the device, so the launch duration that matters for the
-                         # roofline is the timed region divided by the launches it retired; the raw
-                         # CUDA-event duration of one launch (which includes time-sharing the SMs with
-                         # C-1 others) is kept as per_launch_*
+            "roofline": {"bound": "hbm", "kernel": "k_rtr_fast / k_rtr_fast2 / k_rtr_cta (persistent trust-region solve)",
+                         # launches of different slots overlap on the device, so the launch duration that matters
+                         # for the roofline is the timed region divided by the launches it retired; the raw
+                         # CUDA-event duration of one launch (which includes time-sharing the SMs) is per_launch_*
                          "achieved": aggregate, "peak": peak, "unit": "GB/s", "frac": aggregate / peak,
                          "per_launch_achieved": achieved, "per_launch_frac": achieved / peak,
                          "peak_source": peak_src, "traffic": ncu_traffic(workload),
-                         "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "kernel_ms": rtr_avg_ms, "effective_kernel_ms": local_ms / args.steps,
-                         # share of the trust-region kernel in a step: from the serial (one batch at a time) steps,
-                         # comparable with ncu's serialised launch list (profiles/r1e_launches_bench_steps2.csv: 99.3 %);
-                         # with C batches in flight a step's event interval also contains the time its small kernels
-                         # wait for SM slots held by the other batches' persistent launches
-                         "kernel_share_of_step": float(np.sum(serial_rtr_ms) / np.sum(serial_ms)) if serial_ms else None,
-                         "kernel_share_of_step_concurrent": float(np.sum(rtr_ms) / np.sum(step_ms)),
-                         "fp64": {"achieved": alg_flops_total / (local_ms * 1e-3) / 1e12, "peak": fp64_peak_tflops,
-                                  "unit": "TFLOP/s", "frac": alg_flops_total / (local_ms * 1e-3) / 1e12 / fp64_peak_tflops,
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches": n_launch,
+                         "kernel_ms": rtr_avg_ms, "effective_kernel_ms": local_ms / n_launch,
+                         "kernel_share_of_region": float(np.sum(rtr_ms)) / (local_ms * max(args.slots, 1)),
+                         "fp64": {"achieved": alg_flops_total / (local_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS,
+                                  "unit": "TFLOP/s",
+                                  "frac": alg_flops_total / (local_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
                                   "note": "algorithmic flops (38 per term + 60 N + 60 per tCG iteration) / region "
-                                          "time vs the measured FP64 FMA peak; the kernel issues ~2.6x that many "
-                                          "FP64 instructions (terms seen from both end nodes, warp-uniform scalars)"},
+                                          "time vs the measured FP64 FMA peak"},
+                         "tcg_iterations_per_s": in_sum / (local_ms * 1e-3),
                          "note": "algorithmic bytes = sum over problems of 72N*outer + 240N*inner: the state a "
                                  "kernel-per-iteration formulation streams through HBM (SURVEY 8d), from the iteration "
                                  "counts actually executed; the persistent kernel keeps that state in registers (traffic "
                                  "= real DRAM bytes per launch from ncu), so the binding resources are FP64 issue and "
-                                 "shuffle/FMA latency (profiles/)"},
+                                 "dependent-instruction latency (profiles/)"},
+            "stream": stream_stats,
+            "shard_bit_identical": shard_ok,
             "cpu_baseline": cpu,
+            "cpu_baseline_reference": cpu_ref,
             "clocks": clocks,
             "stats": {"converged_frac": stats["converged"] / max(stats["count"], 1),
                       "mean_outer_iters": stats["sum_outer"] / max(stats["count"], 1),
                       "mean_inner_iters": stats["sum_inner"] / max(stats["count"], 1),
                       "max_outer_iters": stats["max_outer"], "mean_f": stats["sum_f"] / max(stats["count"], 1)},
+            "configs": configs,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_configs(args, dev):
+    """The other BASELINE.json configs that fit one GPU and the 1k..64k batch-size sweep of north_star, each measured
+    like the headline (stream of batches, inputs resident in HBM, host wall time between device synchronisations) and
+    each with its own clock record."""
+    import torch
+    from graphik_b200.solvers.riemannian_solver import RiemannianSolver
+    plan = [  # (label, robot, batch, steps)
+        ("BASELINE configs[2]: KUKA-IIWA + table_environment(), 16384 goals, obstacle semantics = reference "
+         "(obstacles are anchors only, SURVEY App. C.1)", "kuka_table", 16384, 1),
+        ("BASELINE configs[3] on one GPU: 20-DOF chain, 65536 goals", "chain20", 65536, 2),
+        ("sweep ur10 1k", "ur10", 1024, 16), ("sweep ur10 16k", "ur10", 16384, 4), ("sweep ur10 64k", "ur10", 65536, 2),
+        ("sweep kuka 1k", "kuka", 1024, 16), ("sweep kuka 4k", "kuka", 4096, 8), ("sweep kuka 16k", "kuka", 16384, 4),
+        ("sweep kuka 64k", "kuka", 65536, 2),
+    ]
+    out = []
+    for label, name, B, K in plan:
+        robot, graph = load_workload(name)
+        solver = RiemannianSolver(graph, {"kernel": args.kernel})
+        eng = solver.engine
+        N = graph.number_of_nodes()
+        Ts = [torch.as_tensor(goals_for(robot, B, seed=5000 + s)[1], device=dev) for s in range(K)]
+        warm = torch.as_tensor(goals_for(robot, min(B, 512), seed=4999)[1], device=dev)
+        measure_stream(solver, [warm], args.slots, None, False)
+        sampler = ClockSampler(dev.index).start()
+        dt, tickets, st = measure_stream(solver, Ts, args.slots, None, False)
+        clocks = sampler.stop()
+        res = [st.result(t) for t in tickets]
+        inner = float(sum(r["n_inner"].sum() for r in res))
+        outer = float(sum(r["iterations"].sum() for r in res))
+        conv = float(sum((r["status"] == 0).sum() for r in res)) / (B * K)
+        alg = 72.0 * N * outer + 240.0 * N * inner
+        peak, _ = measured_peak_hbm()
+        flops = inner * (38.0 * eng.plan.n_terms + 60.0 * N + 60.0)
+        out.append({"workload": label, "robot": name, "batch": B, "steps": K, "nodes": N, "value": B * K / dt,
+                    "unit": UNIT, "seconds": dt, "converged_frac": conv, "streaming_frac": alg / dt / 1e9 / peak,
+                    "fp64_frac": flops / dt / 1e12 / FP64_PEAK_TFLOPS, "tcg_iterations_per_s": inner / dt,
+                    "clocks": clocks})
+        del solver, eng, Ts, res, tickets, st
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baselines(args, robot, graph, n_warm):
+    """cpu_baseline (port) and cpu_baseline_reference (the unmodified reference) on bounded samples of the first timed
+    batch, timed on this box's host cores."""
+    from oracle import ref_arm
+    cpu, cpu_ref = None, None
+    port = CpuPort(robot, graph)
+    sample = args.cpu_sample or 1024
+    _, Tc = goals_for(robot, sample, seed=1000 + n_warm)
+    port.solve(Tc[:64])                                # warm the OpenMP pool and the workers
+    dt, res = port.solve(Tc)
+    cpu = {"value": sample / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
+           "sample": "first " + port.describe(sample, 1) + "; median outer iters %d" % int(np.median(res["iterations"]))}
+    port.close()
+    if args.cpu_kind != "port" and ref_arm.reference_root() is not None:
+        try:
+            ref = CpuReference(args.robot)
+            sample = 4 * ref.cores
+            _, Tr = goals_for(robot, sample, seed=1000 + n_warm)
+            dt, res = ref.solve(Tr)
+            cpu_ref = {"value": sample / dt, "unit": UNIT, "cores": ref.cores, "kind": "reference",
+                       "sample": "first " + ref.describe(sample, 1) + "; pose error < 1e-2 m on %.2f of the goals"
+                                 % float(np.mean(res["pos_err"] < 1e-2))}
+            ref.close()
+        except Exception as e:
+            cpu_ref = {"unavailable": str(e)[:200]}
+    return cpu, cpu_ref
 
 
 if __name__ == "__main__":

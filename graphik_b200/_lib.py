@@ -13,7 +13,8 @@ LIBDIR = os.path.join(_HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libgraphik_b200.so")
 SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_rtr_cta.cu", "gik_bounds_init.cu", "gik_joints.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static"]
 
 
 class GikError(RuntimeError):
@@ -36,18 +37,36 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into graphik_b200/lib/libgraphik_b200.so."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA source for sm_100a into graphik_b200/lib/libgraphik_b200.so (one nvcc process
+    per source file, then one link).  `defines` / `out` build a variant library for A/B experiments
+    (tools/); the product always loads LIBPATH."""
+    out = out or LIBPATH
+    if not force and out == LIBPATH and not needs_build():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIBPATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
+    from concurrent.futures import ThreadPoolExecutor
+    tag = "" if out == LIBPATH else "_" + os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(LIBDIR, "obj" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    dflags = ["-D" + d for d in defines]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + dflags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise GikError("nvcc failed on %s:\n%s\n%s" % (src, res.stdout, res.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [_nvcc()] + LINK_FLAGS + ["-o", out] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise GikError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
-    return LIBPATH
+        raise GikError("nvcc link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return out
 
 
 class PlanDesc(ctypes.Structure):
@@ -63,6 +82,8 @@ class PlanDesc(ctypes.Structure):
         ("goal_edge_i", ctypes.c_void_p), ("goal_edge_j", ctypes.c_void_p), ("goal_edge_slot", ctypes.c_void_p),
         ("omega", ctypes.c_void_p),
         ("n_joints", ctypes.c_int32), ("T0", ctypes.c_void_p),
+        ("n_limits", ctypes.c_int32), ("limit_i", ctypes.c_void_p), ("limit_j", ctypes.c_void_p),
+        ("limit_lower", ctypes.c_void_p), ("limit_upper", ctypes.c_void_p),
     ]
 
 
@@ -73,7 +94,7 @@ class SolveOpts(ctypes.Structure):
         ("rho_prime", ctypes.c_double), ("rho_regularization", ctypes.c_double),
         ("mininner", ctypes.c_int32), ("maxinner", ctypes.c_int32),
         ("Delta_bar", ctypes.c_double), ("Delta0", ctypes.c_double),
-        ("kernel", ctypes.c_int32),
+        ("kernel", ctypes.c_int32), ("maxtime", ctypes.c_double),
     ]
 
 
@@ -82,6 +103,7 @@ EXPORTS = [
     "gik_last_error", "gik_version", "gik_default_opts", "gik_plan_create", "gik_plan_destroy",
     "gik_plan_info", "gik_goal_distances", "gik_cost_grad", "gik_hessvec", "gik_proj", "gik_bounds",
     "gik_init", "gik_bounds_init", "gik_rtr_solve", "gik_joints", "gik_fk", "gik_check_limits",
+    "gik_carry_bytes", "gik_carry_init", "gik_rtr_solve_sliced", "gik_workspace_bytes",
 ]
 
 _lib = None
@@ -92,11 +114,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    override = os.environ.get("GRAPHIK_B200_LIB")   # experiments: load an alternative build of the same ABI
-    if override:
-        global LIBPATH
-        LIBPATH = override
-    elif needs_build():
+    if needs_build():
         try:
             build()
         except (GikError, OSError) as e:
@@ -121,18 +139,25 @@ def load():
         "gik_cost_grad": [vp, vp, vp, i32, vp, vp, vp],
         "gik_hessvec": [vp, vp, vp, vp, i32, vp, vp],
         "gik_proj": [i32, vp, vp, i32, vp, vp],
-        "gik_bounds": [vp, vp, i32, vp, vp, vp],
-        "gik_init": [vp, vp, vp, i32, vp, vp],
-        "gik_bounds_init": [vp, vp, i32, vp, vp],
+        "gik_bounds": [vp, vp, i32, vp, vp, vp, vp],
+        "gik_init": [vp, vp, vp, i32, vp, vp, vp],
+        "gik_bounds_init": [vp, vp, i32, vp, vp, vp],
         "gik_rtr_solve": [vp, vp, vp, i32, ctypes.POINTER(SolveOpts), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
+        "gik_carry_init": [vp, vp, i32, vp],
+        "gik_rtr_solve_sliced": [vp, vp, vp, i32, ctypes.POINTER(SolveOpts), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp,
+                                 vp, vp],
         "gik_joints": [vp, vp, vp, i32, vp, vp],
         "gik_fk": [vp, vp, i32, vp, vp, vp],
-        "gik_check_limits": [vp, vp, dbl, i32, vp, vp],
+        "gik_check_limits": [vp, vp, dbl, i32, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = args
+    L.gik_carry_bytes.restype = ctypes.c_int64
+    L.gik_carry_bytes.argtypes = [vp, i32]
+    L.gik_workspace_bytes.restype = ctypes.c_int64
+    L.gik_workspace_bytes.argtypes = [vp]
     _lib = L
     return L
 

@@ -553,7 +553,7 @@ __global__ void k_bounds_init(const BiArgs a)
 
 size_t small_bytes(int N) { return (size_t)gik_bi_small_doubles(N) * sizeof(double); }
 
-int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
+int launch(const GikPlan *p, BiArgs &a, void *workspace, cudaStream_t st)
 {
     const int N = p->N;
     a.N = N;
@@ -575,23 +575,26 @@ int launch(const GikPlan *p, BiArgs &a, cudaStream_t st)
     size_t smem = small_bytes(N) + (p->bi_mode == 0 ? 3 : (p->bi_mode == 1 ? 2 : 0)) * mat;
     // measured on B200: N = 16: 32 threads 3.9 k goals / ms (64 threads: 3.2 k); N = 44, 65 536 goals: 128 threads
     // 371 ms, 256 threads 479 ms (96 registers: 5 vs 2 CTAs / SM); N = 118 (one CTA / SM): 256 threads 5.8 goals / ms, 512: 7.9
-    int threads = N <= 20 ? 32 : (N <= 64 ? 128 : 512);
-    if (const char *t = getenv("GIK_BI_THREADS")) threads = atoi(t);   // experiments
+    const int threads = N <= 20 ? 32 : (N <= 64 ? 128 : 512);
     int blocks = a.B;
     a.use_scratch = p->bi_mode;
-    a.scratch = p->bi_scratch;
-    if (p->bi_mode && !p->bi_scratch) {
-        gik_set_error("gik_bounds/gik_init: plan for N=%d was created without bound tables (no scratch)", N);
+    a.scratch = static_cast<double *>(workspace);
+    if (p->bi_mode && !workspace) {
+        gik_set_error("gik_bounds/gik_init/gik_bounds_init: a plan with N=%d needs a workspace of gik_workspace_bytes() "
+                      "bytes (one per concurrently running call)", N);
         return GIK_EINVAL;
     }
-    GIK_CUDA(cudaFuncSetAttribute(k_bounds_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int cap = p->bi_blocks;
-    if (p->bi_mode == 0) {
+    // shared-memory opt-in and occupancy depend on (device, N) only: looked up once per plan geometry
+    static int cached_dev = -1, cached_N = -1, cached_cap = 0;
+    if (cached_dev != p->device || cached_N != N) {
+        GIK_CUDA(cudaFuncSetAttribute(k_bounds_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounds_init, threads, smem));
-        if (per_sm < 1) per_sm = 1;
-        cap = p->sm_count * per_sm;
+        cached_cap = p->sm_count * (per_sm < 1 ? 1 : per_sm);
+        cached_dev = p->device;
+        cached_N = N;
     }
+    const int cap = p->bi_mode == 0 ? cached_cap : p->bi_blocks;
     if (blocks > cap) blocks = cap;
     k_bounds_init<<<blocks, threads, smem, st>>>(a);
     return gik_check_cuda(cudaGetLastError(), "k_bounds_init launch");
@@ -610,7 +613,8 @@ int check_device(const GikPlan *p, const char *fn)
 
 }  // namespace
 
-extern "C" int gik_bounds(const GikPlan *p, const double *goal_d2, int32_t B, double *lb, double *ub, void *stream)
+extern "C" int gik_bounds(const GikPlan *p, const double *goal_d2, int32_t B, double *lb, double *ub, void *workspace,
+                          void *stream)
 {
     if (B == 0) return GIK_OK;
     if (!p || !lb || !ub || B < 0 || (!goal_d2 && p->n_goal_edges > 0)) { gik_set_error("gik_bounds: bad argument"); return GIK_EINVAL; }
@@ -623,10 +627,11 @@ extern "C" int gik_bounds(const GikPlan *p, const double *goal_d2, int32_t B, do
     a.B = B;
     a.lb_out = lb;
     a.ub_out = ub;
-    return launch(p, a, (cudaStream_t)stream);
+    return launch(p, a, workspace, (cudaStream_t)stream);
 }
 
-extern "C" int gik_init(const GikPlan *p, const double *lb, const double *ub, int32_t B, double *Y_init, void *stream)
+extern "C" int gik_init(const GikPlan *p, const double *lb, const double *ub, int32_t B, double *Y_init, void *workspace,
+                        void *stream)
 {
     if (B == 0) return GIK_OK;
     if (!p || !lb || !ub || !Y_init || B < 0) { gik_set_error("gik_init: bad argument"); return GIK_EINVAL; }
@@ -637,10 +642,11 @@ extern "C" int gik_init(const GikPlan *p, const double *lb, const double *ub, in
     a.ub_in = ub;
     a.B = B;
     a.Y_init = Y_init;
-    return launch(p, a, (cudaStream_t)stream);
+    return launch(p, a, workspace, (cudaStream_t)stream);
 }
 
-extern "C" int gik_bounds_init(const GikPlan *p, const double *goal_d2, int32_t B, double *Y_init, void *stream)
+extern "C" int gik_bounds_init(const GikPlan *p, const double *goal_d2, int32_t B, double *Y_init, void *workspace,
+                               void *stream)
 {
     if (B == 0) return GIK_OK;
     if (!p || !goal_d2 || !Y_init || B < 0) { gik_set_error("gik_bounds_init: bad argument"); return GIK_EINVAL; }
@@ -652,5 +658,13 @@ extern "C" int gik_bounds_init(const GikPlan *p, const double *goal_d2, int32_t 
     a.do_bounds = 1;
     a.B = B;
     a.Y_init = Y_init;
-    return launch(p, a, (cudaStream_t)stream);
+    return launch(p, a, workspace, (cudaStream_t)stream);
+}
+
+// Bytes of the per-call workspace of gik_bounds / gik_init / gik_bounds_init: 0 while the three N x N matrices of
+// a goal fit in shared memory (N <= 96), else the spilled matrices of every resident CTA.
+extern "C" int64_t gik_workspace_bytes(const GikPlan *p)
+{
+    if (!p || !p->bi_mode) return 0;
+    return (int64_t)p->bi_blocks * (p->bi_mode == 1 ? 1 : 3) * p->N * p->N * (int64_t)sizeof(double);
 }

@@ -157,7 +157,7 @@ k_costs_fast(int N, int n_goal, const uint32_t *__restrict__ fast_info, const do
             const uint32_t gs = GIK_SLOT_GOAL(info[s]);
             const double T = gs ? goal[gs - 1] : tstat[s];
             const double dx = x[0] - P[j], dy = x[1] - P[NPW + j], dz = x[2] - P[2 * NPW + j];
-            const double d = dx * dx + dy * dy + dz * dz;
+            const double d = gik_sqdist(dx, dy, dz);
             double r = d - T;
             const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (r < 0.0)) |
                              ((kind == GIK_TERM_UP) & (r > 0.0));

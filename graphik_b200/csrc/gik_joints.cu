@@ -179,49 +179,38 @@ __global__ void k_fk(int N, int n, int n_anchor, const int32_t *__restrict__ anc
     }
 }
 
-// graph_base.py:219-260 (intended semantics): one thread per problem over the bounded edges.
-__global__ void k_check_limits(int N, int maxdeg, const uint32_t *__restrict__ slot_info,
-                               const int32_t *__restrict__ deg, const double *__restrict__ bs_lower,
-                               const double *__restrict__ bs_upper, const double *__restrict__ Y, double tol,
-                               int B, int32_t *__restrict__ n_broken)
+// graph_base.py:219-260 (intended semantics): one thread per problem over the limit edges.
+__global__ void k_check_limits(int N, int n_limits, const int32_t *__restrict__ li, const int32_t *__restrict__ lj,
+                               const double *__restrict__ lo, const double *__restrict__ up,
+                               const double *__restrict__ Y, double tol, int B, int32_t *__restrict__ n_broken,
+                               int32_t *__restrict__ status)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double *Yb = Y + (size_t)b * N * 3;
     int count = 0;
-    for (int i = 0; i < N; ++i) {
-        const int dg = deg[i];
-        for (int k = 0; k < dg; ++k) {
-            const uint32_t info = slot_info[(size_t)k * N + i];
-            const int j = GIK_SLOT_NBR(info);
-            const uint32_t kind = GIK_SLOT_KIND(info);
-            if (kind == GIK_TERM_EQ || kind > GIK_TERM_UP || j <= i) continue;
-            bool seen = false;   // an edge with both a lower and an upper term is checked once
-            for (int k2 = 0; k2 < k; ++k2) {
-                const uint32_t i2 = slot_info[(size_t)k2 * N + i];
-                seen |= GIK_SLOT_NBR(i2) == (uint32_t)j && GIK_SLOT_KIND(i2) != GIK_TERM_EQ;
-            }
-            if (seen) continue;
-            const double dx = Yb[3 * i] - Yb[3 * j], dy = Yb[3 * i + 1] - Yb[3 * j + 1],
-                         dz = Yb[3 * i + 2] - Yb[3 * j + 2];
-            const double d = sqrt(dx * dx + dy * dy + dz * dz);
-            count += d < bs_lower[(size_t)i * N + j] - tol;
-            count += d > bs_upper[(size_t)i * N + j] + tol;
-        }
+    for (int k = 0; k < n_limits; ++k) {
+        const int i = li[k], j = lj[k];
+        const double dx = Yb[3 * i] - Yb[3 * j], dy = Yb[3 * i + 1] - Yb[3 * j + 1], dz = Yb[3 * i + 2] - Yb[3 * j + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        count += d < lo[k] - tol;
+        count += d > up[k] + tol;
     }
     n_broken[b] = count;
+    if (status && count > 0 && (status[b] == GIK_STATUS_CONVERGED || status[b] == GIK_STATUS_MAXITER))
+        status[b] = GIK_STATUS_LIMITS;
 }
 
 }  // namespace
 
 extern "C" int gik_check_limits(const GikPlan *p, const double *Y, double tol, int32_t B, int32_t *n_broken,
-                                void *stream)
+                                int32_t *status, void *stream)
 {
     if (B == 0) return GIK_OK;
     if (!p || !Y || !n_broken || B < 0) { gik_set_error("gik_check_limits: bad argument"); return GIK_EINVAL; }
-    if (!p->bs_lower || !p->bs_upper) { gik_set_error("gik_check_limits: plan was created without bound tables"); return GIK_EINVAL; }
-    k_check_limits<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->N, p->maxdeg, p->slot_info, p->deg,
-                                                                    p->bs_lower, p->bs_upper, Y, tol, B, n_broken);
+    k_check_limits<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->N, p->n_limits, p->limit_i, p->limit_j,
+                                                                    p->limit_lower, p->limit_upper, Y, tol, B,
+                                                                    n_broken, status);
     return gik_check_cuda(cudaGetLastError(), "k_check_limits launch");
 }
 

@@ -46,6 +46,7 @@ extern "C" int gik_default_opts(GikSolveOpts *o)
     o->Delta_bar = 13.0;             // fixed_rank_psd_sym.py:72 (10 + k)
     o->Delta0 = 13.0 / 8;            // trust_region.py:137-138
     o->kernel = GIK_KERNEL_AUTO;
+    o->maxtime = 1000.0;             // pymanopt Solver default (trust_region.py:103 passes none)
     return GIK_OK;
 }
 
@@ -337,14 +338,6 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         const size_t cap = 227 * 1024;
         p->bi_mode = small + 3 * mat <= cap ? 0 : (small + 2 * mat <= cap ? 1 : 2);
         p->bi_blocks = p->bi_mode == 1 ? p->sm_count : 2 * p->sm_count;
-        p->bi_scratch = nullptr;
-        if (p->bi_mode) {
-            const size_t count = (size_t)p->bi_blocks * (p->bi_mode == 1 ? 1 : 3) * N * N;
-            if (gik_check_cuda(cudaMalloc((void **)&p->bi_scratch, count * sizeof(double)), "cudaMalloc(bi_scratch)")) {
-                delete p;
-                return GIK_ECUDA;
-            }
-        }
     }
 
     bool ok = true;
@@ -378,6 +371,17 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     ok = ok && !upload(&p->omega_j, oj.data(), oj.size());
     ok = ok && !upload(&p->omega_ptr, optr.data(), optr.size());
     ok = ok && !upload(&p->omega_adj, oadj.data(), oadj.size());
+    p->n_limits = (d->n_limits > 0 && d->limit_i && d->limit_j && d->limit_lower && d->limit_upper) ? d->n_limits : 0;
+    for (int k = 0; k < p->n_limits; ++k)
+        if (d->limit_i[k] < 0 || d->limit_i[k] >= N || d->limit_j[k] < 0 || d->limit_j[k] >= N) {
+            gik_set_error("gik_plan_create: bad limit edge %d", k);
+            gik_plan_destroy(p);
+            return GIK_EINVAL;
+        }
+    ok = ok && !upload(&p->limit_i, d->limit_i, (size_t)p->n_limits);
+    ok = ok && !upload(&p->limit_j, d->limit_j, (size_t)p->n_limits);
+    ok = ok && !upload(&p->limit_lower, d->limit_lower, (size_t)p->n_limits);
+    ok = ok && !upload(&p->limit_upper, d->limit_upper, (size_t)p->n_limits);
     if (d->n_joints > 0 && d->T0) {
         ok = ok && !upload(&p->T0, d->T0, (size_t)(d->n_joints + 1) * 16);
         ok = ok && !upload(&p->Trel, Trel.data(), Trel.size());
@@ -392,9 +396,9 @@ extern "C" int gik_plan_destroy(GikPlan *p)
 {
     if (!p) return GIK_OK;
     void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_hub_kind, p->dense_hub_target, p->dense_goal_i, p->dense_goal_j,
-                    p->dense_goal_slot, p->bi_scratch, p->anchor_node, p->anchor_pos, p->bs_lower,
+                    p->dense_goal_slot, p->anchor_node, p->anchor_pos, p->bs_lower,
                     p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_ptr, p->omega_adj, p->omega_i,
-                    p->omega_j, p->T0, p->Trel, p->qs0};
+                    p->omega_j, p->T0, p->Trel, p->qs0, p->limit_i, p->limit_j, p->limit_lower, p->limit_upper};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     delete p;

@@ -28,6 +28,8 @@
 #include <cstdlib>
 
 #include "gik_common.cuh"
+#include <cstdint>
+
 #include "gik_rtr.cuh"
 
 namespace {
@@ -102,33 +104,61 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
 
+    // parked problems of the incoming queue are resumed before any new problem starts (gik_rtr.cuh)
+    int n_res = 0;
+    if (a.carry_in) {
+        const GikCarryHdr *h = reinterpret_cast<const GikCarryHdr *>(a.carry_in);
+        n_res = min(h->count, h->capacity);
+    }
+
     for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(a.work_counter, 1);
-        b = __shfl_sync(mask, b, leader, 32);
-        if (b >= a.B) break;
+        int w = 0;
+        if (lane == 0) w = atomicAdd(a.work_counter, 1);
+        w = __shfl_sync(mask, w, leader, 32);
+        if (w >= n_res + a.B) break;
+        const bool resumed = w < n_res;
+        const int b = w - n_res;
+        const double *ent = resumed ? gik_carry_entry(a.carry_in, w) : nullptr;
+        const unsigned long long *entp = reinterpret_cast<const unsigned long long *>(ent);
+        const double *goal_row = resumed ? reinterpret_cast<const double *>(entp[CW_GOAL])
+                                         : a.goal_d2 + (size_t)b * a.n_goal;
 
         double x[NPL][3], g[NPL][3], eta[NPL][3], Heta[NPL][3], r[NPL][3], dl[NPL][3], Hd[NPL][3];
         // ---- load the problem
         {
-            const double *src = a.Y_init + (size_t)b * 3 * a.N;
+            const double *src = resumed ? ent + CW_X : a.Y_init + (size_t)b * 3 * a.N;
 #pragma unroll
             for (int m = 0; m < NPL; ++m) {
                 const int i = lane + W * m;
+                g[m][0] = g[m][1] = g[m][2] = 0.0;
                 if (i < a.N) {
                     x[m][0] = src[3 * i]; x[m][1] = src[3 * i + 1]; x[m][2] = src[3 * i + 2];
+                    if (resumed) {
+                        const double *gs = src + 3 * a.N;
+                        g[m][0] = gs[3 * i]; g[m][1] = gs[3 * i + 1]; g[m][2] = gs[3 * i + 2];
+                    }
                 } else {
                     x[m][0] = x[m][1] = x[m][2] = 0.0;
                 }
             }
             __syncwarp(mask);
-            for (int k = lane; k < a.n_goal; k += W) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
+            for (int k = lane; k < a.n_goal; k += W) goal[k] = goal_row[k];
             gik_publish<W, NPL>(c.P, x, lane);
             __syncwarp(mask);
         }
         // fx = cost(x); fgradx = grad(x); norm_grad (trust_region.py:158-160)
-        double fx, gg, Mi[6];
-        {
+        double fx, gg, Mi[6], Delta;
+        int k_outer, inner_total;
+        unsigned long long t0;
+        if (resumed) {
+            fx = ent[CW_FX]; gg = ent[CW_GG]; Delta = ent[CW_DELTA];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Mi[k] = ent[CW_MI + k];
+            const unsigned long long cnt = entp[CW_COUNTS];
+            k_outer = (int)(cnt & 0xffffffffu);
+            inner_total = (int)(cnt >> 32);
+            t0 = entp[CW_T0];
+        } else {
             double v[8];
             v[0] = gik_pass_cost_grad<W, NPL>(c, x, g);
             v[1] = dot3<NPL>(g, g);
@@ -137,10 +167,17 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
             fx = v[0];
             gg = v[1];
             gik_sylvester_inverse(v + 2, Mi);
+            Delta = o.Delta0;
+            k_outer = 0;
+            inner_total = 0;
+            t0 = a.maxtime_ns ? gik_globaltimer() : 0ull;
+            t0 = __shfl_sync(mask, t0, leader, 32);
         }
+        const int inner_entry = inner_total;
+        bool may_park = a.carry_out != nullptr;
+        int park_slot = -1;
         double norm_grad = sqrt(gg);
-        double Delta = o.Delta0;
-        int k_outer = 0, inner_total = 0, status = GIK_STATUS_MAXITER;
+        int status = GIK_STATUS_MAXITER;
         if (!(isfinite(fx) && isfinite(gg))) {
             status = GIK_STATUS_NAN;
         } else {
@@ -301,7 +338,7 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
                     gik_publish<W, NPL>(c.P, x, lane);
                     __syncwarp(mask);
                 }
-                if (a.trace && k_outer < a.trace_rows && lane == 0) {
+                if (a.trace && !resumed && k_outer < a.trace_rows && lane == 0) {
                     double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
                     row[0] = Delta_used;
                     row[1] = (double)numit;
@@ -311,27 +348,43 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
                     row[5] = accept ? norm_grad : nan("");
                 }
                 ++k_outer;
-                // pymanopt Solver._check_stopping_criterion: maxiter before mingradnorm
+                // pymanopt Solver._check_stopping_criterion: maxtime, then maxiter, then mingradnorm
+                if (a.maxtime_ns) {
+                    unsigned long long now = gik_globaltimer() - t0;
+                    now = __shfl_sync(mask, now, leader, 32);
+                    if (now >= a.maxtime_ns) { status = GIK_STATUS_MAXTIME; break; }
+                }
                 if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
+                if (may_park && inner_total - inner_entry >= a.inner_budget) {
+                    if (lane == 0) park_slot = gik_carry_reserve(a.carry_out);
+                    park_slot = __shfl_sync(mask, park_slot, leader, 32);
+                    if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
+                    may_park = false;   // queue full: run this problem to its end
+                }
             }
         }
-        // ---- store optlog final_values
+        // ---- store optlog final_values (or, for a parked problem, its current ones and its queue entry)
         {
-            double *dst = a.Y_out + (size_t)b * 3 * a.N;
+            double *dst = resumed ? reinterpret_cast<double *>(entp[CW_Y]) : a.Y_out + (size_t)b * 3 * a.N;
+            double *cx = status == GIK_STATUS_PENDING ? gik_carry_slot(a.carry_out, park_slot) : nullptr;
 #pragma unroll
             for (int m = 0; m < NPL; ++m) {
                 const int i = lane + W * m;
                 if (i < a.N) {
                     dst[3 * i] = x[m][0]; dst[3 * i + 1] = x[m][1]; dst[3 * i + 2] = x[m][2];
+                    if (cx) {
+                        double *cd = cx + CW_X + 3 * i;
+                        cd[0] = x[m][0]; cd[1] = x[m][1]; cd[2] = x[m][2];
+                        cd += 3 * a.N;
+                        cd[0] = g[m][0]; cd[1] = g[m][1]; cd[2] = g[m][2];
+                    }
                 }
             }
             if (lane == 0) {
-                a.f[b] = fx;
-                a.gradnorm[b] = norm_grad;
-                a.iters[b] = k_outer;
-                a.status[b] = status;
-                if (a.n_inner) a.n_inner[b] = inner_total;
+                const double sg[3] = {0.0, 0.0, 0.0};   // only k_rtr_fast / k_rtr_fast2 carry sum g_i x Y_i
+                gik_finish_problem(a, resumed, b, entp, goal_row, cx, t0, status, k_outer, inner_total, fx, gg,
+                                   norm_grad, Delta, Mi, sg, dst);
             }
         }
         __syncwarp(mask);
@@ -359,7 +412,7 @@ int launch_rtr(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     if (per_sm < 1) per_sm = 1;
     int blocks = p->sm_count * per_sm;
     const int need = (a.B + GPB - 1) / GPB;
-    if (blocks > need) blocks = need;
+    if (!a.carry_in && blocks > need) blocks = need;   // the number of parked problems is only known on the device
     GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
     k_rtr<W, NPL><<<blocks, kThreads, smem, st>>>(a);
     return gik_check_cuda(cudaGetLastError(), "k_rtr launch");
@@ -367,48 +420,21 @@ int launch_rtr(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 
 }  // namespace
 
-extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const double *Y_init, int32_t B,
-                             const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
-                             int32_t *iters, int32_t *status, int32_t *n_inner, double *trace,
-                             int32_t trace_rows, int32_t *work_counter, void *stream)
+// Kernel selection shared by gik_rtr_solve and gik_rtr_solve_sliced.  k_rtr_fast and k_rtr_duo return the same bits
+// (gik_tr_math.cuh), so for N <= 16 the choice between them is free per launch: two problems per warp where the
+// device is kept full (large one-piece batches, the bulk launches of a sliced stream), one problem per warp where
+// the wall time is the slowest problem (small batches, draining launches).
+static int rtr_dispatch(const GikPlan *p, RtrArgs &a, bool sliced, cudaStream_t st)
 {
-    if (B == 0) return GIK_OK;
-    if (!p || !Y_init || !Y_out || !f || !gradnorm || !iters || !status || !work_counter || B < 0 ||
-        (p->n_goal > 0 && !goal_d2)) {
-        gik_set_error("gik_rtr_solve: bad argument");
-        return GIK_EINVAL;
-    }
-    int dev = -1;
-    cudaGetDevice(&dev);
-    if (dev != p->device) {
-        gik_set_error("gik_rtr_solve: plan belongs to device %d but device %d is current", p->device, dev);
-        return GIK_EINVAL;
-    }
-    if (B == 0) return GIK_OK;
-    RtrArgs a;
-    a.slot_info = p->slot_info;
-    a.slot_target = p->slot_target;
-    a.deg = p->deg;
-    a.N = p->N;
-    a.n_goal = p->n_goal;
-    a.maxdeg = p->maxdeg;
-    a.tables_in_smem = 0;
-    a.goal_d2 = goal_d2;
-    a.Y_init = Y_init;
-    a.B = B;
-    if (opts) a.o = *opts; else gik_default_opts(&a.o);
-    if (a.o.maxiter < 1 || a.o.maxinner < 1) { gik_set_error("gik_rtr_solve: maxiter/maxinner must be >= 1"); return GIK_EINVAL; }
-    a.Y_out = Y_out; a.f = f; a.gradnorm = gradnorm; a.iters = iters; a.status = status; a.n_inner = n_inner;
-    a.trace = trace; a.trace_rows = trace ? trace_rows : 0; a.work_counter = work_counter;
-    cudaStream_t st = (cudaStream_t)stream;
-    // implementation choice (all three run the same algorithm): GIK_RTR_GENERIC=1 / opts->kernel
     int kernel = a.o.kernel;
-    const char *force = getenv("GIK_RTR_GENERIC");
-    if (force && force[0] == '1') kernel = GIK_KERNEL_GENERIC;
     if (kernel == GIK_KERNEL_AUTO) {
-        if (p->N <= 32) kernel = (B >= 49152 && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
-        else kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE
-                      : (p->fast2_info ? GIK_KERNEL_LATENCY : GIK_KERNEL_GENERIC);
+        if (p->N <= 32) {
+            const bool bulk = sliced ? (a.B > 0 && a.carry_out != nullptr) : a.B > 32768;
+            kernel = (bulk && p->duo_info) ? GIK_KERNEL_THROUGHPUT : GIK_KERNEL_LATENCY;
+        } else {
+            kernel = (p->dense_target && 8 * (long)p->n_terms >= (long)p->N * p->N) ? GIK_KERNEL_DENSE
+                     : (p->fast2_info ? GIK_KERNEL_LATENCY : GIK_KERNEL_GENERIC);
+        }
     }
     if (kernel == GIK_KERNEL_DENSE) {
         const int rc = gik_launch_rtr_cta(p, a, st);
@@ -432,4 +458,104 @@ extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const doub
         case 2: return launch_rtr<32, 2>(p, a, st);
         default: return launch_rtr<32, 4>(p, a, st);
     }
+}
+
+static int rtr_fill_args(const char *fn, const GikPlan *p, const double *goal_d2, const double *Y_init, int32_t B,
+                         const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm, int32_t *iters,
+                         int32_t *status, int32_t *n_inner, int32_t *work_counter, RtrArgs &a)
+{
+    if (!p || !work_counter || B < 0 ||
+        (B > 0 && (!Y_init || !Y_out || !f || !gradnorm || !iters || !status || (p->n_goal > 0 && !goal_d2)))) {
+        gik_set_error("%s: bad argument", fn);
+        return GIK_EINVAL;
+    }
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != p->device) {
+        gik_set_error("%s: plan belongs to device %d but device %d is current", fn, p->device, dev);
+        return GIK_EINVAL;
+    }
+    a.slot_info = p->slot_info;
+    a.slot_target = p->slot_target;
+    a.deg = p->deg;
+    a.N = p->N;
+    a.n_goal = p->n_goal;
+    a.maxdeg = p->maxdeg;
+    a.tables_in_smem = 0;
+    a.goal_d2 = goal_d2;
+    a.Y_init = Y_init;
+    a.B = B;
+    if (opts) a.o = *opts; else gik_default_opts(&a.o);
+    if (a.o.maxiter < 1 || a.o.maxinner < 1) { gik_set_error("%s: maxiter/maxinner must be >= 1", fn); return GIK_EINVAL; }
+    a.Y_out = Y_out; a.f = f; a.gradnorm = gradnorm; a.iters = iters; a.status = status; a.n_inner = n_inner;
+    a.trace = nullptr; a.trace_rows = 0; a.work_counter = work_counter;
+    a.inner_budget = 0; a.carry_in = nullptr; a.carry_out = nullptr; a.pending = nullptr;
+    a.maxtime_ns = a.o.maxtime > 0.0 ? (unsigned long long)(a.o.maxtime * 1e9) : 0ull;
+    return GIK_OK;
+}
+
+extern "C" int gik_rtr_solve(const GikPlan *p, const double *goal_d2, const double *Y_init, int32_t B,
+                             const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
+                             int32_t *iters, int32_t *status, int32_t *n_inner, double *trace,
+                             int32_t trace_rows, int32_t *work_counter, void *stream)
+{
+    if (B == 0) return GIK_OK;
+    RtrArgs a;
+    if (int rc = rtr_fill_args("gik_rtr_solve", p, goal_d2, Y_init, B, opts, Y_out, f, gradnorm, iters, status,
+                               n_inner, work_counter, a))
+        return rc;
+    a.trace = trace;
+    a.trace_rows = trace ? trace_rows : 0;
+    return rtr_dispatch(p, a, false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// deferred stragglers
+
+namespace {
+__global__ void k_carry_init(GikCarryHdr *h, int capacity, int stride)
+{
+    h->count = 0; h->capacity = capacity; h->stride = stride; h->full = 0;
+}
+}  // namespace
+
+extern "C" int64_t gik_carry_bytes(const GikPlan *p, int32_t capacity)
+{
+    if (!p || capacity < 0) return 0;
+    return (int64_t)sizeof(GikCarryHdr) + (int64_t)capacity * gik_carry_stride(p->N) * (int64_t)sizeof(double);
+}
+
+extern "C" int gik_carry_init(const GikPlan *p, void *carry, int32_t capacity, void *stream)
+{
+    if (!p || !carry || capacity < 0) { gik_set_error("gik_carry_init: bad argument"); return GIK_EINVAL; }
+    if ((uintptr_t)carry % 16) { gik_set_error("gik_carry_init: the buffer must be 16-byte aligned"); return GIK_EINVAL; }
+    k_carry_init<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<GikCarryHdr *>(carry), capacity, gik_carry_stride(p->N));
+    return gik_check_cuda(cudaGetLastError(), "k_carry_init launch");
+}
+
+extern "C" int gik_rtr_solve_sliced(const GikPlan *p, const double *goal_d2, const double *Y_init, int32_t B,
+                                    const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
+                                    int32_t *iters, int32_t *status, int32_t *n_inner, int32_t inner_budget,
+                                    const void *carry_in, void *carry_out, int32_t *pending,
+                                    int32_t *work_counter, void *stream)
+{
+    if (B == 0 && !carry_in) return GIK_OK;
+    RtrArgs a;
+    if (int rc = rtr_fill_args("gik_rtr_solve_sliced", p, goal_d2, Y_init, B, opts, Y_out, f, gradnorm, iters,
+                               status, n_inner, work_counter, a))
+        return rc;
+    if (carry_in && carry_in == carry_out) {
+        gik_set_error("gik_rtr_solve_sliced: carry_in and carry_out must be different buffers");
+        return GIK_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    a.carry_in = static_cast<const char *>(carry_in);
+    if (carry_out && inner_budget > 0) {
+        a.carry_out = static_cast<char *>(carry_out);
+        a.inner_budget = inner_budget;
+        a.pending = pending;
+    }
+    if (carry_out)   // empty the outgoing queue (capacity, stride and the `full` statistic stay)
+        GIK_CUDA(cudaMemsetAsync(carry_out, 0, sizeof(int32_t), st));
+    return rtr_dispatch(p, a, true, st);
 }

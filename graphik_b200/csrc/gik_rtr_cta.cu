@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
     double *Hc2 = Tq + NPAD;                            // [NPAD] 2 act (d - T) of the second terms around the hub node
     double *goal = Hc2 + NPAD;                          // [n_goal]
-    int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));
+    int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));                    // [0] work item, [1] park slot
+    unsigned long long *s_t = reinterpret_cast<unsigned long long *>(s_b + 2);          // [0] problem start, [1] elapsed
     const int gp = tb.gp, gq = tb.gq;
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;
@@ -336,19 +337,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         return f;
     };
 
+    // parked problems of the incoming queue are resumed before any new problem starts (gik_rtr.cuh)
+    int n_res = 0;
+    if (a.carry_in) {
+        const GikCarryHdr *h = reinterpret_cast<const GikCarryHdr *>(a.carry_in);
+        n_res = min(h->count, h->capacity);
+    }
+
     for (;;) {
         if (tid == 0) s_b[0] = atomicAdd(a.work_counter, 1);
         __syncthreads();
-        const int b = s_b[0];
+        const int w = s_b[0];
         __syncthreads();
-        if (b >= a.B) break;
+        if (w >= n_res + a.B) break;
+        const bool resumed = w < n_res;
+        const int b = w - n_res;
+        const double *ent = resumed ? gik_carry_entry(a.carry_in, w) : nullptr;
+        const unsigned long long *entp = reinterpret_cast<const unsigned long long *>(ent);
+        const double *goal_row = resumed ? reinterpret_cast<const double *>(entp[CW_GOAL])
+                                         : a.goal_d2 + (size_t)b * a.n_goal;
 
         double x[3] = {0.0, 0.0, 0.0}, g[3] = {0.0, 0.0, 0.0}, eta[3], Heta[3], r[3], dl[3], Hd[3] = {0.0, 0.0, 0.0};
         if (owner) {
-            const double *src = a.Y_init + ((size_t)b * N + tid) * 3;
+            const double *src = resumed ? ent + CW_X + 3 * tid : a.Y_init + ((size_t)b * N + tid) * 3;
             x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
+            if (resumed) {
+                src = ent + CW_X + 3 * (N + tid);
+                g[0] = src[0]; g[1] = src[1]; g[2] = src[2];
+            }
         }
-        for (int k = tid; k < a.n_goal; k += kThreads) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
+        for (int k = tid; k < a.n_goal; k += kThreads) goal[k] = goal_row[k];
         publish(P2, x, 2.0);
         if (gp >= 0) {
             for (int i = tid; i < N; i += kThreads) {
@@ -367,8 +385,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         }
         __syncthreads();
 
-        double fx, gg, Mi[6];
-        {
+        double fx, gg, Mi[6], Delta;
+        int k_outer, inner_total;
+        if (resumed) {
+            fx = ent[CW_FX]; gg = ent[CW_GG]; Delta = ent[CW_DELTA];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Mi[k] = ent[CW_MI + k];
+            const unsigned long long cnt = entp[CW_COUNTS];
+            k_outer = (int)(cnt & 0xffffffffu);
+            inner_total = (int)(cnt >> 32);
+            if (tid == 0) s_t[0] = entp[CW_T0];
+            pair_pass_cost();   // tile, pair cache and activity masks at x, as after a rejected step
+        } else {
             pair_pass_cost();
             __syncthreads();
             if (owner) gather(g);
@@ -381,10 +409,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
             fx = total_cost();
             gg = v[0];
             gik_sylvester_inverse(v + 1, Mi);
+            Delta = o.Delta0;
+            k_outer = 0;
+            inner_total = 0;
+            if (tid == 0) s_t[0] = a.maxtime_ns ? gik_globaltimer() : 0ull;
         }
+        const int inner_entry = inner_total;
+        bool may_park = a.carry_out != nullptr;
+        int park_slot = -1;
         double norm_grad = sqrt(gg);
-        double Delta = o.Delta0;
-        int k_outer = 0, inner_total = 0, status = GIK_STATUS_MAXITER;
+        int status = GIK_STATUS_MAXITER;
         if (!(isfinite(fx) && isfinite(gg))) {
             status = GIK_STATUS_NAN;
         } else {
@@ -531,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                     __syncthreads();
                     pair_pass_cost();
                 }
-                if (a.trace && k_outer < a.trace_rows && tid == 0) {
+                if (a.trace && !resumed && k_outer < a.trace_rows && tid == 0) {
                     double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
                     row[0] = Delta_used;
                     row[1] = (double)numit;
@@ -541,20 +575,42 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                     row[5] = accept ? norm_grad : nan("");
                 }
                 ++k_outer;
+                // pymanopt Solver._check_stopping_criterion: maxtime, then maxiter, then mingradnorm
+                if (a.maxtime_ns) {
+                    __syncthreads();
+                    if (tid == 0) s_t[1] = gik_globaltimer() - s_t[0];
+                    __syncthreads();
+                    if (s_t[1] >= a.maxtime_ns) { status = GIK_STATUS_MAXTIME; break; }
+                }
                 if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
+                if (may_park && inner_total - inner_entry >= a.inner_budget) {
+                    __syncthreads();
+                    if (tid == 0) s_b[1] = gik_carry_reserve(a.carry_out);
+                    __syncthreads();
+                    park_slot = s_b[1];
+                    if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
+                    may_park = false;   // queue full: run this problem to its end
+                }
             }
         }
+        // ---- final values (or, for a parked problem, its current ones) go where the problem came from
+        double *Yrow = resumed ? reinterpret_cast<double *>(entp[CW_Y]) : a.Y_out + (size_t)b * N * 3;
+        double *cx = status == GIK_STATUS_PENDING ? gik_carry_slot(a.carry_out, park_slot) : nullptr;
         if (owner) {
-            double *dst = a.Y_out + ((size_t)b * N + tid) * 3;
+            double *dst = Yrow + tid * 3;
             dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
+            if (cx) {
+                dst = cx + CW_X + 3 * tid;
+                dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
+                dst += 3 * N;
+                dst[0] = g[0]; dst[1] = g[1]; dst[2] = g[2];
+            }
         }
         if (tid == 0) {
-            a.f[b] = fx;
-            a.gradnorm[b] = norm_grad;
-            a.iters[b] = k_outer;
-            a.status[b] = status;
-            if (a.n_inner) a.n_inner[b] = inner_total;
+            const double sg[3] = {0.0, 0.0, 0.0};   // only the warp kernels carry sum g_i x Y_i
+            gik_finish_problem(a, resumed, b, entp, goal_row, cx, s_t[0], status, k_outer, inner_total, fx, gg,
+                               norm_grad, Delta, Mi, sg, Yrow);
         }
         __syncthreads();
     }
@@ -564,7 +620,7 @@ size_t cta_smem_bytes(int N, int n_goal)
 {
     const int goal_pad = (n_goal + 1) & ~1;
     size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 3) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
-                      sizeof(double) + 2 * sizeof(int);
+                      sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned long long);
     return (smem + 15) & ~(size_t)15;
 }
 
@@ -574,12 +630,18 @@ template <int NB>
 static int launch_cta(const GikPlan *p, RtrArgs &a, const CtaTables &tb, size_t smem, cudaStream_t st)
 {
     auto kern = k_rtr_cta<NB>;
-    GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    int blocks = p->sm_count * per_sm;
-    if (blocks > a.B) blocks = a.B;
+    static size_t cached_smem = ~(size_t)0;
+    static int cached_per_sm = 0, cached_dev = -1;
+    if (cached_smem != smem || cached_dev != p->device) {
+        GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+        cached_per_sm = per_sm < 1 ? 1 : per_sm;
+        cached_smem = smem;
+        cached_dev = p->device;
+    }
+    int blocks = p->sm_count * cached_per_sm;
+    if (!a.carry_in && blocks > a.B) blocks = a.B;
     GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
     kern<<<blocks, kThreads, smem, st>>>(a, tb);
     return gik_check_cuda(cudaGetLastError(), "k_rtr_cta launch");

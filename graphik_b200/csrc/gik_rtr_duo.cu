@@ -1,82 +1,63 @@
-// gik_rtr_duo.cu -- throughput-optimised trust-region solve for graphs with N <= 16 nodes:
-// TWO problems per warp advancing in lock-step.
+// gik_rtr_duo.cu -- throughput kernel for graphs with N <= 16 nodes: TWO problems per warp.
 //
-// Same algorithm and arithmetic conventions as k_rtr_fast / k_rtr (reference
-// trust_region.py:112-599, costs.py:79-207, fixed_rank_psd_sym.py:91-137).  k_rtr_fast spends a
-// whole warp on one problem (best latency for the slowest problem of a batch); when many problems
-// are queued the limiter is instruction issue (ncu, UR10 B = 65536: 381 warp instructions per inner
-// iteration, IPC 0.47 per scheduler).  Here each half-warp owns one problem, lane <-> node, and the
-// inner tCG iteration is written as straight-line code that BOTH halves execute together, so one
-// instruction stream serves two problems:
+// Same algorithm as k_rtr_fast (reference trust_region.py:112-599, costs.py:79-207,
+// fixed_rank_psd_sym.py:91-137) and -- through gik_tr_math.cuh -- the same floating-point operations in
+// the same order: a problem solved here, by k_rtr_fast<2, S> or partly by one and partly by the other
+// (gik_rtr_solve_sliced parks and resumes problems across launches) ends with the same bits.
 //
-//   * every shuffle in the inner iteration uses xor offsets <= 8 and the full mask, hence stays
-//     inside a half and is executed once per warp;
-//   * the three ways a tCG iteration can end (boundary / negative curvature, model increase,
-//     target reached) only set the half's phase; state commits are per-lane predicated;
-//   * what happens once per outer iteration (proposal cost/gradient, rho test, radius update,
-//     accept/reject, start of the next subproblem) and once per problem (fetch from the work
-//     queue, initial cost/gradient, final store) runs in short divergent sections guarded by a
-//     warp vote, ~2 of every 70 ticks per half;
-//   * the x-dependent part of each edge term (2 act D, 2 act r) is cached per accepted iterate in
-//     SHARED memory ([slot][lane], conflict-free) instead of registers: with one lane per node a lane
-//     has up to 12 slots, and the loads do not depend on delta, so they are off the critical path.
+// k_rtr_fast spends a whole warp on one problem: best for the critical path of a single problem, but
+// half of its instructions compute values every lane of the warp already has (the scalar recurrences
+// of tCG, the 3 x 3 projection, the reductions).  Here each HALF-warp owns one problem, lane <-> node,
+// and one instruction stream serves both:
+//
+//   * the inner tCG iteration is straight-line code executed by both halves together; its two
+//     reductions go through shared memory once for both problems (gik_warp.cuh: node_allreduce_s
+//     layout, 4 lanes per (half, scalar)); the three ways an iteration can end only set the half's
+//     phase, state commits are per-lane predicated;
+//   * what happens once per outer iteration (proposal cost / gradient, rho test, radius update,
+//     accept / reject, parking) and once per problem (fetch from the queue or from the carry queue,
+//     initial cost / gradient, final store) runs in divergent sections guarded by a warp vote;
+//   * a lane evaluates ALL slots of its node (k_rtr_fast<2, S> splits them over two lanes) but keeps
+//     the two lanes' accumulator chains apart (slot k goes to chain k & 1) and adds them at the end --
+//     exactly the sum k_rtr_fast forms with its pair shuffle, and twice the instruction-level
+//     parallelism in the slot loop;
+//   * the x-dependent part of each term (2 act D, 2 act r) is cached per accepted iterate in shared
+//     memory ([slot][2][lane] double2, conflict-free); the loads do not depend on delta.
 //
 // A half whose phase is not INNER executes the inner block on dead state; nothing it computes is
-// committed or stored.
+// committed or stored.  A stalled problem (short tCG runs) makes its partner wait during its outer
+// sections -- that costs latency, not throughput: the instructions issued per step are the same as for
+// two separate warps.  The kernel is therefore used where latency is hidden: large one-piece batches
+// and the bulk launches of gik_rtr_solve_sliced; small batches and draining launches use k_rtr_fast.
 #include <cstdlib>
 
 #include "gik_rtr.cuh"
+#include "gik_tr_math.cuh"
+#include "gik_warp.cuh"
 
 namespace {
 
 constexpr int kThreads = 32;
+constexpr int kRS = 34;   // row stride of the reduction buffer: 128-bit reads of a quarter-warp hit disjoint banks
 enum { PH_NEED_PROBLEM = 0, PH_NEED_OUTER = 1, PH_INNER = 2, PH_IDLE = 3 };
 
-// transposed butterfly over the 16 lanes of each half (offsets 8, 4, 2, 1), full-warp mask
-template <int KP>
-__device__ __forceinline__ void half_allreduce_t(double (&v)[KP], int lane)
-{
-    static_assert(KP == 4 || KP == 8, "KP must be 4 or 8");
-    double cur[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) cur[k] = v[k];
-    int cnt = KP;
-#pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
-        if (cnt > 1) {
-            const int half = cnt / 2;
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int k = 0; k < KP / 2; ++k) {
-                if (k < half) {
-                    const double keep = up ? cur[half + k] : cur[k];
-                    const double send = up ? cur[k] : cur[half + k];
-                    cur[k] = keep + __shfl_xor_sync(GIK_FULL_MASK, send, off, 32);
-                }
-            }
-            cnt = half;
-        } else {
-            cur[0] += __shfl_xor_sync(GIK_FULL_MASK, cur[0], off, 32);
-        }
-    }
-    const int base = lane & 16;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int src = (KP == 8) ? (((k >> 2) & 1) * 8 + ((k >> 1) & 1) * 4 + (k & 1) * 2)
-                                  : (((k >> 1) & 1) * 8 + (k & 1) * 4);
-        v[k] = __shfl_sync(GIK_FULL_MASK, cur[0], base + src, 32);
-    }
-}
-
-// plain butterfly inside one half with the half's own mask (divergent sections)
+// plain butterfly inside one half (lane = node: neighbours, quads, eights, all sixteen -- the tree of
+// node_allreduce_s / node_allreduce_b over 16 node columns), used by the divergent sections
 template <int K>
 __device__ __forceinline__ void half_allreduce(double (&v)[K], unsigned gmask)
 {
 #pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
+    for (int off = 1; off <= 8; off <<= 1) {
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(gmask, v[k], off, 32);
     }
+}
+
+__host__ __device__ constexpr int duo_smem_doubles(int SPL, int goal_pad)
+{
+    // P, V [3][32]; goal rows of the two halves; per-problem slot targets [SPL][32]; slot cache [SPL][2][32] double2;
+    // reduction rows [4][kRS] + totals [8]; start times [2]
+    return 192 + 2 * goal_pad + SPL * 32 + SPL * 128 + 4 * kRS + 8 + 2;
 }
 
 template <int SPL>
@@ -87,127 +68,189 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
     const int lane = threadIdx.x & 31;
     const int node = lane & 15;
     const int hbase = lane & 16;                       // first lane of this half
+    const int half = lane >> 4;
     const unsigned gmask = hbase ? 0xffff0000u : 0x0000ffffu;
     const bool valid = node < a.N;
     const int goal_pad = (a.n_goal + 1) & ~1;
-    // per-warp shared memory: P[3][32], V[3][32], goal[2][goal_pad], tgt[SPL][32], cache[SPL][4][32]
     double *P = smem;
     double *V = P + 96;
-    double *goal = V + 96 + (hbase ? goal_pad : 0);
-    double *tgt = V + 96 + 2 * goal_pad + lane;
-    double *cache = V + 96 + 2 * goal_pad + SPL * 32 + lane;
+    double *goal = V + 96 + half * goal_pad;
+    double *tgt = V + 96 + 2 * goal_pad + lane;                                               // [SPL][32]
+    double2 *scm = reinterpret_cast<double2 *>(V + 96 + 2 * goal_pad + SPL * 32) + lane;      // [SPL][2][32]
+    double *R = V + 96 + 2 * goal_pad + SPL * 32 + SPL * 128;
+    double *Tt = R + 4 * kRS;
+    unsigned long long *t_start = reinterpret_cast<unsigned long long *>(Tt + 8) + half;
     const GikSolveOpts &o = a.o;
-    const double eps = 2.220446049250313e-16;  // np.spacing(1), trust_region.py:293
 
-    // static slot description of this lane; neighbour indices are rebased into this half's buffers
-    uint32_t info[SPL];
+    // static slot description of this lane; neighbour addresses are rebased into this half's exchange columns
+    uint32_t vj[SPL];
+    uint32_t kinds = 0;
 #pragma unroll
-    for (int s = 0; s < SPL; ++s) info[s] = duo_info[s * 16 + node];
+    for (int s = 0; s < SPL; ++s) {
+        const uint32_t info = duo_info[s * 16 + node];
+        vj[s] = gik_saddr(V + hbase + GIK_SLOT_NBR(info));
+        kinds |= GIK_SLOT_KIND(info) << (2 * s);
+    }
+    const uint32_t vown = gik_saddr(V + lane);
+    constexpr int PO = -96 * 8, CS = 32 * 8;   // byte offsets: V -> P, coordinate stride
+    // reduction addresses: every lane deposits into column `lane`; lane L sums 4 nodes of row (L >> 2) & 3 of its half
+    const uint32_t r_dep = gik_saddr(R + lane);
+    const uint32_t r_src = gik_saddr(R + ((lane >> 2) & 3) * kRS + hbase + (lane & 3) * 4);
+    const uint32_t r_dst = gik_saddr(Tt + half * 4 + ((lane >> 2) & 3));
+    const uint32_t r_tot = gik_saddr(Tt + half * 4);
+    const bool r_writer = (lane & 3) == 0;
+    // all-reduce of 4 scalars over the 16 nodes of EACH half at once; same tree as node_allreduce_s<2, 4>
+    auto reduce4 = [&](double (&v)[4]) {
+        gik_sts<0 * kRS * 8>(r_dep, v[0]); gik_sts<1 * kRS * 8>(r_dep, v[1]);
+        gik_sts<2 * kRS * 8>(r_dep, v[2]); gik_sts<3 * kRS * 8>(r_dep, v[3]);
+        __syncwarp();
+        const double2 p0 = gik_lds2<0>(r_src), p1 = gik_lds2<16>(r_src);
+        double s = __dadd_rn(__dadd_rn(p0.x, p0.y), __dadd_rn(p1.x, p1.y));
+        s += __shfl_xor_sync(GIK_FULL_MASK, s, 1, 32);
+        s += __shfl_xor_sync(GIK_FULL_MASK, s, 2, 32);
+        if (r_writer) gik_sts<0>(r_dst, s);
+        __syncwarp();
+        const double2 t0 = gik_lds2<0>(r_tot), t1 = gik_lds2<16>(r_tot);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+    };
 
     double x[3] = {0, 0, 0}, g[3] = {0, 0, 0}, eta[3] = {0, 0, 0}, Heta[3] = {0, 0, 0}, r[3] = {0, 0, 0},
            dl[3] = {0, 0, 0}, Hd[3];
-    double fx = 0, gg = 0, norm_grad = 0, Mi[6] = {0, 0, 0, 0, 0, 0}, Delta = 0, Delta2 = 0;
-    double e_Pe = 0, r_r = 1, z_r = 1, inv_z_r = 1, d_Pd = 1, e_Pd = 0, model_value = 0, r_target2 = 0, pw = 0;
-    int b = 0, phase = PH_NEED_PROBLEM, k_outer = 0, inner_total = 0, status = 0, stop = MAX_INNER_ITER, j = 0,
-        numit = 0;
+    double fx = 0, gg = 0, norm_grad = 0, Mi[6] = {0, 0, 0, 0, 0, 0}, sg[3] = {0, 0, 0}, u[3] = {0, 0, 0}, Delta = 0;
+    double e_Pe = 0, z_r = 1, inv_z_r = 1, d_Pd = 1, e_Pd = 0, model_value = 0;
+    trm::TcgStart ts = {0, 0, 0, 1};
+    int w = 0, phase = PH_NEED_PROBLEM, k_outer = 0, inner_total = 0, inner_entry = 0, status = 0,
+        stop = MAX_INNER_ITER, j = 0, numit = 0;
+    bool may_park = false;
 
-    // cost / gradient at p (published in P) + rebuild of the slot cache; returns this lane's cost share
+    int n_res = 0;
+    if (a.carry_in) {
+        const GikCarryHdr *h = reinterpret_cast<const GikCarryHdr *>(a.carry_in);
+        n_res = min(h->count, h->capacity);
+    }
+
+    // cost / gradient at p (published in P) + rebuild of the slot cache; returns the node's cost share.
+    // Slot k accumulates into chain k & 1: the two lanes of k_rtr_fast<2, S>.
     auto rebuild = [&](const double (&p)[3], double (&gout)[3]) -> double {
-        double fpart = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+        double fpart[2] = {0.0, 0.0}, gacc[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
-            const int jn = hbase + (int)GIK_SLOT_NBR(info[s]);
-            const uint32_t kind = GIK_SLOT_KIND(info[s]);
-            const double dx = p[0] - P[jn], dy = p[1] - P[32 + jn], dz = p[2] - P[64 + jn];
-            const double d = dx * dx + dy * dy + dz * dz;
-            double rr = d - tgt[s * 32];
-            const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (rr < 0.0)) |
-                             ((kind == GIK_TERM_UP) & (rr > 0.0));
-            rr = act ? rr : 0.0;
-            fpart = fma(rr, rr, fpart);
-            gx = fma(rr, dx, gx);
-            gy = fma(rr, dy, gy);
-            gz = fma(rr, dz, gz);
-            const double two = act ? 2.0 : 0.0;
-            cache[(s * 4 + 0) * 32] = two * dx;
-            cache[(s * 4 + 1) * 32] = two * dy;
-            cache[(s * 4 + 2) * 32] = two * dz;
-            cache[(s * 4 + 3) * 32] = 2.0 * rr;
+            const uint32_t kind = (kinds >> (2 * s)) & 3u;
+            const double dx = trm::sub(p[0], gik_lds<PO>(vj[s])), dy = trm::sub(p[1], gik_lds<PO + CS>(vj[s])),
+                         dz = trm::sub(p[2], gik_lds<PO + 2 * CS>(vj[s]));
+            const trm::SlotEval e = trm::slot_cost(dx, dy, dz, tgt[s * 32], kind, fpart[s & 1], gacc[s & 1]);
+            scm[(s * 2 + 0) * 32] = make_double2(trm::mul(e.two, dx), trm::mul(e.two, dy));
+            scm[(s * 2 + 1) * 32] = make_double2(trm::mul(e.two, dz), trm::mul(2.0, e.rr));
         }
-        gout[0] = 2.0 * gx; gout[1] = 2.0 * gy; gout[2] = 2.0 * gz;
-        return 0.5 * fpart;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) gout[q] = trm::add(trm::mul(2.0, gacc[0][q]), trm::mul(2.0, gacc[1][q]));
+        return trm::add(trm::mul(0.5, fpart[0]), trm::mul(0.5, fpart[1]));
     };
 
     // start of a trust-region subproblem (trust_region.py:436-490), eta0 = 0, precon = identity
     auto start_tcg = [&]() {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { eta[q] = 0.0; Heta[q] = 0.0; r[q] = g[q]; dl[q] = -g[q]; }
-        e_Pe = 0.0;
-        r_r = gg;
-        const double norm_r0 = sqrt(r_r);
-        z_r = r_r; d_Pd = r_r; e_Pd = 0.0; model_value = 0.0;
-        pw = o.theta == 1.0 ? norm_r0 : pow(norm_r0, o.theta);
-        const double r_target = norm_r0 * fmin(pw, o.kappa);
-        r_target2 = r_target * r_target;
-        Delta2 = Delta * Delta;
-        inv_z_r = gik_rcp(z_r);
+        for (int q = 0; q < 3; ++q) { eta[q] = 0.0; Heta[q] = 0.0; r[q] = g[q]; dl[q] = -g[q]; u[q] = -sg[q]; }
+        ts = trm::tcg_start(gg, Delta, o);
+        e_Pe = 0.0; z_r = gg; d_Pd = gg; e_Pd = 0.0; model_value = 0.0; inv_z_r = ts.inv_z_r;
         stop = MAX_INNER_ITER;
         j = 0;
     };
 
-    auto store_result = [&]() {
+    // the problem of this half leaves the warp: final values, or its state into the outgoing queue (park_slot >= 0)
+    auto leave_problem = [&](int park_slot) {
+        const bool resumed = w < n_res;
+        const int b = w - n_res;
+        const double *ent = resumed ? gik_carry_entry(a.carry_in, w) : nullptr;
+        const unsigned long long *entp = reinterpret_cast<const unsigned long long *>(ent);
+        double *Yrow = resumed ? reinterpret_cast<double *>(entp[CW_Y]) : a.Y_out + (size_t)b * a.N * 3;
+        double *cx = park_slot >= 0 ? gik_carry_slot(a.carry_out, park_slot) : nullptr;
         if (valid) {
-            double *dst = a.Y_out + ((size_t)b * a.N + node) * 3;
+            double *dst = Yrow + node * 3;
             dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
+            if (cx) {
+                dst = cx + CW_X + 3 * node;
+                dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
+                dst += 3 * a.N;
+                dst[0] = g[0]; dst[1] = g[1]; dst[2] = g[2];
+            }
         }
         if (node == 0) {
-            a.f[b] = fx;
-            a.gradnorm[b] = norm_grad;
-            a.iters[b] = k_outer;
-            a.status[b] = status;
-            if (a.n_inner) a.n_inner[b] = inner_total;
+            const double *goal_row = resumed ? reinterpret_cast<const double *>(entp[CW_GOAL])
+                                             : a.goal_d2 + (size_t)b * a.n_goal;
+            gik_finish_problem(a, resumed, b, entp, goal_row, cx, *t_start, status, k_outer, inner_total, fx, gg,
+                               norm_grad, Delta, Mi, sg, Yrow);
         }
     };
 
     for (;;) {
-        // ================= A. halves without a problem pull the next one from the queue
+        // ================= A. halves without a problem pull the next one: parked problems first, then new ones
         if (__any_sync(GIK_FULL_MASK, phase == PH_NEED_PROBLEM)) {
             if (phase == PH_NEED_PROBLEM) {
-                int nb = 0;
-                if (node == 0) nb = atomicAdd(a.work_counter, 1);
-                b = __shfl_sync(gmask, nb, hbase, 32);
-                if (b >= a.B) {
+                int nw = 0;
+                if (node == 0) nw = atomicAdd(a.work_counter, 1);
+                w = __shfl_sync(gmask, nw, hbase, 32);
+                if (w >= n_res + a.B) {
                     phase = PH_IDLE;
                 } else {
+                    const bool resumed = w < n_res;
+                    const int b = w - n_res;
+                    const double *ent = resumed ? gik_carry_entry(a.carry_in, w) : nullptr;
+                    const unsigned long long *entp = reinterpret_cast<const unsigned long long *>(ent);
+                    const double *goal_row = resumed ? reinterpret_cast<const double *>(entp[CW_GOAL])
+                                                     : a.goal_d2 + (size_t)b * a.n_goal;
                     x[0] = x[1] = x[2] = 0.0;
+                    g[0] = g[1] = g[2] = 0.0;
                     if (valid) {
-                        const double *src = a.Y_init + ((size_t)b * a.N + node) * 3;
+                        const double *src = resumed ? ent + CW_X + 3 * node : a.Y_init + ((size_t)b * a.N + node) * 3;
                         x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
+                        if (resumed) {
+                            src = ent + CW_X + 3 * (a.N + node);
+                            g[0] = src[0]; g[1] = src[1]; g[2] = src[2];
+                        }
                     }
-                    for (int k = node; k < a.n_goal; k += 16) goal[k] = a.goal_d2[(size_t)b * a.n_goal + k];
-                    P[lane] = x[0]; P[32 + lane] = x[1]; P[64 + lane] = x[2];
+                    for (int k = node; k < a.n_goal; k += 16) goal[k] = goal_row[k];
+                    gik_sts<PO>(vown, x[0]); gik_sts<PO + CS>(vown, x[1]); gik_sts<PO + 2 * CS>(vown, x[2]);
                     __syncwarp(gmask);
 #pragma unroll
                     for (int s = 0; s < SPL; ++s) {
-                        const uint32_t gs = GIK_SLOT_GOAL(info[s]);
+                        const uint32_t gs = GIK_SLOT_GOAL(duo_info[s * 16 + node]);
                         tgt[s * 32] = gs ? goal[gs - 1] : duo_target[s * 16 + node];
                     }
-                    double v[8];
-                    v[0] = rebuild(x, g);
-                    v[1] = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
-                    v[2] = x[0] * x[0]; v[3] = x[0] * x[1]; v[4] = x[0] * x[2];
-                    v[5] = x[1] * x[1]; v[6] = x[1] * x[2]; v[7] = x[2] * x[2];
-                    half_allreduce<8>(v, gmask);
-                    fx = v[0];
-                    gg = v[1];
-                    gik_sylvester_inverse(v + 2, Mi);
+                    if (resumed) {
+                        fx = ent[CW_FX]; gg = ent[CW_GG]; Delta = ent[CW_DELTA];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) Mi[k] = ent[CW_MI + k];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) sg[k] = ent[CW_SG + k];
+                        const unsigned long long cnt = entp[CW_COUNTS];
+                        k_outer = (int)(cnt & 0xffffffffu);
+                        inner_total = (int)(cnt >> 32);
+                        if (node == 0) *t_start = entp[CW_T0];
+                        double gtmp[3];
+                        rebuild(x, gtmp);   // slot cache at x, as after a rejected step
+                    } else {
+                        double v[16];
+                        v[0] = rebuild(x, g);
+                        trm::point_scalars(x, g, v + 1);
+#pragma unroll
+                        for (int k = 11; k < 16; ++k) v[k] = 0.0;
+                        half_allreduce<11>(reinterpret_cast<double (&)[11]>(v), gmask);
+                        fx = v[0];
+                        gg = v[1];
+                        gik_sylvester_inverse(v + 2, Mi);
+                        sg[0] = v[8]; sg[1] = v[9]; sg[2] = v[10];
+                        Delta = o.Delta0;
+                        k_outer = 0;
+                        inner_total = 0;
+                        if (node == 0) *t_start = a.maxtime_ns ? gik_globaltimer() : 0ull;
+                    }
+                    inner_entry = inner_total;
+                    may_park = a.carry_out != nullptr;
                     norm_grad = sqrt(gg);
-                    Delta = o.Delta0;
-                    k_outer = 0;
-                    inner_total = 0;
                     if (!(isfinite(fx) && isfinite(gg))) {
                         status = GIK_STATUS_NAN;
-                        store_result();          // stays PH_NEED_PROBLEM: fetch again next tick
+                        leave_problem(-1);       // stays PH_NEED_PROBLEM: fetch again next tick
                     } else {
                         status = GIK_STATUS_MAXITER;
                         start_tcg();
@@ -222,50 +265,38 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
         // ================= B. halves whose subproblem ended: proposal, rho test, accept / reject
         if (__any_sync(GIK_FULL_MASK, phase == PH_NEED_OUTER)) {
             if (phase == PH_NEED_OUTER) {
-                double xp[3], gp[3];
+                double xp[3], gp[3], v[16];
+                v[11] = trm::dot3(g, eta);
+                v[12] = trm::dot3(eta, Heta);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) xp[q] = x[q] + eta[q];
-                P[lane] = xp[0]; P[32 + lane] = xp[1]; P[64 + lane] = xp[2];
+                for (int q = 0; q < 3; ++q) xp[q] = trm::add(x[q], eta[q]);
+                gik_sts<PO>(vown, xp[0]); gik_sts<PO + CS>(vown, xp[1]); gik_sts<PO + 2 * CS>(vown, xp[2]);
                 __syncwarp(gmask);
-                double v[10];
                 v[0] = rebuild(xp, gp);
-                v[1] = g[0] * eta[0] + g[1] * eta[1] + g[2] * eta[2];
-                v[2] = eta[0] * Heta[0] + eta[1] * Heta[1] + eta[2] * Heta[2];
-                v[3] = gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2];
-                v[4] = xp[0] * xp[0]; v[5] = xp[0] * xp[1]; v[6] = xp[0] * xp[2];
-                v[7] = xp[1] * xp[1]; v[8] = xp[1] * xp[2]; v[9] = xp[2] * xp[2];
-                half_allreduce<10>(v, gmask);
+                trm::point_scalars(xp, gp, v + 1);
+                half_allreduce<13>(reinterpret_cast<double (&)[13]>(v), gmask);
                 const double fx_prop = v[0];
-                double rhonum = fx - fx_prop;
-                double rhoden = -v[1] - 0.5 * v[2];
-                const double rho_reg = fmax(1.0, fabs(fx)) * eps * o.rho_regularization;
-                rhonum += rho_reg;
-                rhoden += rho_reg;
-                const bool model_decreased = rhoden >= 0.0;
-                const double rho = rhonum / rhoden;
                 const double Delta_used = Delta;
-                if (rho < 0.25 || !model_decreased || isnan(rho)) {
-                    Delta = Delta / 4.0;
-                } else if (rho > 0.75 && (stop == NEGATIVE_CURVATURE || stop == EXCEEDED_TR)) {
-                    Delta = fmin(2.0 * Delta, o.Delta_bar);
-                }
-                const bool accept = model_decreased && rho > o.rho_prime;
+                const trm::OuterDecision od = trm::outer_decision(fx, fx_prop, v[11], v[12], Delta, stop, o);
+                Delta = od.Delta;
+                const bool accept = od.accept;
                 if (accept) {
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { x[q] = xp[q]; g[q] = gp[q]; }
                     fx = fx_prop;
-                    gg = v[3];
+                    gg = v[1];
                     norm_grad = sqrt(gg);
-                    gik_sylvester_inverse(v + 4, Mi);
+                    gik_sylvester_inverse(v + 2, Mi);
+                    sg[0] = v[8]; sg[1] = v[9]; sg[2] = v[10];
                 } else {
                     __syncwarp(gmask);
-                    P[lane] = x[0]; P[32 + lane] = x[1]; P[64 + lane] = x[2];
+                    gik_sts<PO>(vown, x[0]); gik_sts<PO + CS>(vown, x[1]); gik_sts<PO + 2 * CS>(vown, x[2]);
                     __syncwarp(gmask);
                     double gtmp[3];
                     rebuild(x, gtmp);
                 }
-                if (a.trace && k_outer < a.trace_rows && node == 0) {
-                    double *row = a.trace + ((size_t)b * a.trace_rows + k_outer) * 6;
+                if (a.trace && w >= n_res && k_outer < a.trace_rows && node == 0) {
+                    double *row = a.trace + ((size_t)(w - n_res) * a.trace_rows + k_outer) * 6;
                     row[0] = Delta_used;
                     row[1] = (double)numit;
                     row[2] = (double)stop;
@@ -274,114 +305,114 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
                     row[5] = accept ? norm_grad : nan("");
                 }
                 ++k_outer;
-                // pymanopt Solver._check_stopping_criterion: maxiter before mingradnorm
-                if (k_outer >= o.maxiter) {
+                // pymanopt Solver._check_stopping_criterion: maxtime, then maxiter, then mingradnorm
+                bool timed_out = false;
+                if (a.maxtime_ns) {
+                    unsigned long long now = 0;
+                    if (node == 0) now = gik_globaltimer() - *t_start;
+                    now = __shfl_sync(gmask, now, hbase, 32);
+                    timed_out = now >= a.maxtime_ns;
+                }
+                if (timed_out) {
+                    status = GIK_STATUS_MAXTIME;
+                    leave_problem(-1);
+                    phase = PH_NEED_PROBLEM;
+                } else if (k_outer >= o.maxiter) {
                     status = GIK_STATUS_MAXITER;
-                    store_result();
+                    leave_problem(-1);
                     phase = PH_NEED_PROBLEM;
                 } else if (norm_grad < o.mingradnorm) {
                     status = GIK_STATUS_CONVERGED;
-                    store_result();
+                    leave_problem(-1);
                     phase = PH_NEED_PROBLEM;
                 } else {
-                    start_tcg();
-                    phase = PH_INNER;
+                    int park_slot = -1;
+                    if (may_park && inner_total - inner_entry >= a.inner_budget) {
+                        if (node == 0) park_slot = gik_carry_reserve(a.carry_out);
+                        park_slot = __shfl_sync(gmask, park_slot, hbase, 32);
+                        if (park_slot < 0) may_park = false;   // queue full: run this problem to its end
+                    }
+                    if (park_slot >= 0) {
+                        status = GIK_STATUS_PENDING;
+                        leave_problem(park_slot);
+                        phase = PH_NEED_PROBLEM;
+                    } else {
+                        start_tcg();
+                        phase = PH_INNER;
+                    }
                 }
             }
             __syncwarp();
         }
 
         // ================= C. one tCG iteration (trust_region.py:495-597), both halves together
-        V[lane] = dl[0]; V[32 + lane] = dl[1]; V[64 + lane] = dl[2];
+        gik_sts<0>(vown, dl[0]); gik_sts<CS>(vown, dl[1]); gik_sts<2 * CS>(vown, dl[2]);
         __syncwarp();
-        double z[3] = {0.0, 0.0, 0.0}, zb[3] = {0.0, 0.0, 0.0};
+        double z[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, zb[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
         for (int s = 0; s < SPL; ++s) {
-            const int jn = hbase + (int)GIK_SLOT_NBR(info[s]);
-            const double cx = cache[(s * 4 + 0) * 32], cy = cache[(s * 4 + 1) * 32], cz = cache[(s * 4 + 2) * 32];
-            const double c2 = cache[(s * 4 + 3) * 32];
-            const double wx = dl[0] - V[jn], wy = dl[1] - V[32 + jn], wz = dl[2] - V[64 + jn];
-            const double t = fma(cx, wx, fma(cy, wy, cz * wz));
-            z[0] = fma(c2, wx, z[0]);
-            z[1] = fma(c2, wy, z[1]);
-            z[2] = fma(c2, wz, z[2]);
-            zb[0] = fma(t, cx, zb[0]);
-            zb[1] = fma(t, cy, zb[1]);
-            zb[2] = fma(t, cz, zb[2]);
+            const double wx = trm::sub(dl[0], gik_lds<0>(vj[s])), wy = trm::sub(dl[1], gik_lds<CS>(vj[s])),
+                         wz = trm::sub(dl[2], gik_lds<2 * CS>(vj[s]));
+            const double2 a0 = scm[(s * 2 + 0) * 32], a1 = scm[(s * 2 + 1) * 32];
+            trm::slot_hess(a0.x, a0.y, a1.x, a1.y, wx, wy, wz, z[s & 1], zb[s & 1]);
         }
-        z[0] += zb[0]; z[1] += zb[1]; z[2] += zb[2];
-        double v[8];
-        v[7] = 0.0;
-        v[0] = dl[0] * z[0] + dl[1] * z[1] + dl[2] * z[2];
-        v[1] = z[1] * x[2] - z[2] * x[1];      // c = sum Z_i x Y_i
-        v[2] = z[2] * x[0] - z[0] * x[2];
-        v[3] = z[0] * x[1] - z[1] * x[0];
-        v[4] = dl[1] * x[2] - dl[2] * x[1];    // u = sum delta_i x Y_i
-        v[5] = dl[2] * x[0] - dl[0] * x[2];
-        v[6] = dl[0] * x[1] - dl[1] * x[0];
-        half_allreduce_t<8>(v, lane);
-        double om[3];
-        gik_sym_mul(Mi, v + 1, om);
-        Hd[0] = z[0] - (x[1] * om[2] - x[2] * om[1]);
-        Hd[1] = z[1] - (x[2] * om[0] - x[0] * om[2]);
-        Hd[2] = z[2] - (x[0] * om[1] - x[1] * om[0]);
-        const double d_Hd = v[0] - (om[0] * v[4] + om[1] * v[5] + om[2] * v[6]);
+        double Z[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) Z[q] = trm::add(trm::add(z[0][q], zb[0][q]), trm::add(z[1][q], zb[1][q]));
+        double v[4];
+        trm::hess_scalars(dl, Z, x, v);
+        reduce4(v);
+        const trm::InnerScalars is = trm::inner_scalars(Mi, v, u, z_r, e_Pe, e_Pd, d_Pd, ts.Delta2);
+        trm::project(Z, x, is.om, Hd);
         inner_total += phase == PH_INNER;
-        const double alpha = gik_div(z_r, d_Hd, gik_rcp(d_Hd));
-        const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
-        // boundary / negative curvature (!(d_Hd > 0) also catches NaN): rare, handled divergently
-        const bool exit1 = phase == PH_INNER && (!(d_Hd > 0.0) || e_Pe_new >= Delta2);
+        // boundary / negative curvature (also a NaN curvature): rare, handled divergently
+        const bool exit1 = phase == PH_INNER && is.leave;
         if (__any_sync(GIK_FULL_MASK, exit1)) {
             if (exit1) {
-                const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;
+                const double tau = trm::boundary_tau(e_Pe, e_Pd, d_Pd, ts.Delta2);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     eta[q] = fma(tau, dl[q], eta[q]);
                     Heta[q] = fma(tau, Hd[q], Heta[q]);
                 }
-                stop = d_Hd <= 0.0 ? NEGATIVE_CURVATURE : EXCEEDED_TR;
+                stop = is.d_Hd <= 0.0 ? NEGATIVE_CURVATURE : EXCEEDED_TR;
                 numit = j;
                 phase = PH_NEED_OUTER;
             }
             __syncwarp();
         }
-        double ne[3], nh[3], nr[3], sdot[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            ne[q] = fma(alpha, dl[q], eta[q]);
-            nh[q] = fma(alpha, Hd[q], Heta[q]);
-            nr[q] = fma(alpha, Hd[q], r[q]);
-            sdot[0] = fma(ne[q], g[q], sdot[0]);
-            sdot[1] = fma(ne[q], nh[q], sdot[1]);
-            sdot[2] = fma(nr[q], nr[q], sdot[2]);
-        }
-        half_allreduce_t<4>(sdot, lane);
-        const double new_model_value = sdot[0] + 0.5 * sdot[1];
+        double ne[3], nh[3], nr[3], sdot[4];
+        trm::inner_step(is.alpha, dl, Hd, eta, Heta, r, g, ne, nh, nr, sdot);
+        reduce4(sdot);
+        const double new_model_value = trm::model_value(sdot);
         const bool cont = phase == PH_INNER;
         const bool model_inc = cont && new_model_value >= model_value;
         const bool commit = cont && !model_inc;
         if (model_inc) { stop = MODEL_INCREASED; numit = j; phase = PH_NEED_OUTER; }
+        const double r_r = sdot[2];
         if (commit) {
-            e_Pe = e_Pe_new;
+            e_Pe = is.e_Pe_new;
 #pragma unroll
             for (int q = 0; q < 3; ++q) { eta[q] = ne[q]; Heta[q] = nh[q]; r[q] = nr[q]; }
             model_value = new_model_value;
-            r_r = sdot[2];
         }
-        const bool reached = commit && j >= o.mininner && r_r <= r_target2;
+        const bool reached = commit && j >= o.mininner && r_r <= ts.r_target2;
         if (reached) {
-            stop = o.kappa < pw ? REACHED_TARGET_LINEAR : REACHED_TARGET_SUPERLINEAR;
+            stop = o.kappa < ts.pw ? REACHED_TARGET_LINEAR : REACHED_TARGET_SUPERLINEAR;
             numit = j;
             phase = PH_NEED_OUTER;
         }
-        const double beta = gik_div(r_r, z_r, inv_z_r);
+        const trm::NextDir nd = trm::next_direction(r_r, z_r, inv_z_r, is.alpha, e_Pd, d_Pd);
         if (commit && !reached) {
             z_r = r_r;
             inv_z_r = gik_rcp(z_r);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) dl[q] = fma(beta, dl[q], -r[q]);
-            e_Pd = beta * (e_Pd + alpha * d_Pd);
-            d_Pd = z_r + beta * beta * d_Pd;
+            for (int q = 0; q < 3; ++q) {
+                dl[q] = fma(nd.beta, dl[q], -r[q]);
+                u[q] = fma(nd.beta, u[q], -sg[q]);
+            }
+            e_Pd = nd.e_Pd;
+            d_Pd = nd.d_Pd;
             ++j;
             if (j >= o.maxinner) { stop = MAX_INNER_ITER; numit = o.maxinner - 1; phase = PH_NEED_OUTER; }
         }
@@ -391,18 +422,25 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
 template <int SPL>
 int launch(const GikPlan *p, RtrArgs &a, cudaStream_t st)
 {
+    auto kern = k_rtr_duo<SPL>;
     const int goal_pad = (p->n_goal + 1) & ~1;
-    const size_t smem = (size_t)(192 + 2 * goal_pad + SPL * 32 + SPL * 4 * 32) * sizeof(double);
-    if (smem > 48 * 1024)
-        GIK_CUDA(cudaFuncSetAttribute(k_rtr_duo<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtr_duo<SPL>, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    int blocks = p->sm_count * per_sm;
+    const size_t smem = (size_t)duo_smem_doubles(SPL, goal_pad) * sizeof(double);
+    static size_t cached_smem = ~(size_t)0;
+    static int cached_per_sm = 0, cached_dev = -1;
+    if (cached_smem != smem || cached_dev != p->device) {
+        if (smem > 48 * 1024)
+            GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+        cached_per_sm = per_sm < 1 ? 1 : per_sm;
+        cached_smem = smem;
+        cached_dev = p->device;
+    }
+    int blocks = p->sm_count * cached_per_sm;
     const int need = (a.B + 1) / 2;
-    if (blocks > need) blocks = need;
+    if (!a.carry_in && blocks > need) blocks = need;   // the number of parked problems is only known on the device
     GIK_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
-    k_rtr_duo<SPL><<<blocks, kThreads, smem, st>>>(a, p->duo_info, p->duo_target);
+    kern<<<blocks, kThreads, smem, st>>>(a, p->duo_info, p->duo_target);
     return gik_check_cuda(cudaGetLastError(), "k_rtr_duo launch");
 }
 

@@ -30,7 +30,7 @@ def make_opts(params=None):
     o = _lib.SolveOpts()
     _lib.check(_lib.load().gik_default_opts(ctypes.byref(o)), "gik_default_opts")
     params = params or {}
-    for key in ("mingradnorm", "theta", "kappa", "rho_prime", "rho_regularization", "Delta_bar", "Delta0"):
+    for key in ("mingradnorm", "theta", "kappa", "rho_prime", "rho_regularization", "Delta_bar", "Delta0", "maxtime"):
         if key in params:
             setattr(o, key, float(params[key]))
     for key in ("maxiter", "mininner", "maxinner"):
@@ -65,7 +65,9 @@ class BatchIK:
         with torch.cuda.device(self.device):
             self.plan = plan if plan is not None else Plan.from_graph(graph, use_limits=use_limits)
         self.opts = make_opts(params)
-        self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._counters = {}   # work-queue counter of gik_rtr_solve per CUDA stream (calls on one stream serialise)
+        self._workspaces = {}
+        self._ws_bytes = int(self.lib.gik_workspace_bytes(self.plan.handle))
         self.launches = 0  # kernels launched through this engine (bench.py's gpu_launches)
 
     # ------------------------------------------------------------------ helpers
@@ -84,6 +86,27 @@ class BatchIK:
     def _empty(self, *shape, dtype=None):
         return self.torch.empty(shape, dtype=dtype or self.torch.float64, device=self.device)
 
+    def _counter(self):
+        """Per-stream scratch for the persistent work queue: two solves issued on different streams from one
+        engine must not share it."""
+        key = self.torch.cuda.current_stream(self.device).cuda_stream
+        c = self._counters.get(key)
+        if c is None:
+            c = self._counters[key] = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+        return c
+
+    def _workspace(self):
+        """Per-stream workspace of the bound-smoothing / initialisation kernel (None while everything fits in
+        shared memory, i.e. N <= 96)."""
+        if not self._ws_bytes:
+            return None
+        key = self.torch.cuda.current_stream(self.device).cuda_stream
+        w = self._workspaces.get(key)
+        if w is None:
+            w = self._workspaces[key] = self.torch.empty(self._ws_bytes // 8, dtype=self.torch.float64,
+                                                         device=self.device)
+        return w
+
     # ------------------------------------------------------------------ stages
     def goal_distances(self, T_goal):
         T = self._f64(T_goal).reshape(-1, 4, 4)
@@ -101,7 +124,8 @@ class BatchIK:
         B = g.shape[0] if g is not None else int(B)
         lb, ub = self._empty(B, N, N), self._empty(B, N, N)
         with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.gik_bounds(self.plan.handle, _p(g), B, _p(lb), _p(ub), self._stream()), "gik_bounds")
+            _lib.check(self.lib.gik_bounds(self.plan.handle, _p(g), B, _p(lb), _p(ub), _p(self._workspace()),
+                                           self._stream()), "gik_bounds")
         self.launches += 1
         return lb, ub
 
@@ -111,7 +135,8 @@ class BatchIK:
         B = lb.shape[0]
         Y = self._empty(B, N, 3)
         with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.gik_init(self.plan.handle, _p(lb), _p(ub), B, _p(Y), self._stream()), "gik_init")
+            _lib.check(self.lib.gik_init(self.plan.handle, _p(lb), _p(ub), B, _p(Y), _p(self._workspace()),
+                                         self._stream()), "gik_init")
         self.launches += 1
         return Y
 
@@ -120,7 +145,8 @@ class BatchIK:
         B, N = g.shape[0], self.plan.N
         Y = self._empty(B, N, 3)
         with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.gik_bounds_init(self.plan.handle, _p(g), B, _p(Y), self._stream()), "gik_bounds_init")
+            _lib.check(self.lib.gik_bounds_init(self.plan.handle, _p(g), B, _p(Y), _p(self._workspace()),
+                                                self._stream()), "gik_bounds_init")
         self.launches += 1
         return Y
 
@@ -177,7 +203,7 @@ class BatchIK:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.gik_rtr_solve(self.plan.handle, _p(g2), _p(Y0), B, ctypes.byref(o), _p(Y), _p(f),
                                               _p(gn), _p(iters), _p(status), _p(n_inner), _p(trace),
-                                              int(trace_rows), _p(self._counter), self._stream()), "gik_rtr_solve")
+                                              int(trace_rows), _p(self._counter()), self._stream()), "gik_rtr_solve")
         self.launches += 2  # memset of the work counter + the persistent kernel
         return {"x": Y, "f(x)": f, "gradnorm": gn, "iterations": iters, "status": status,
                 "n_inner": n_inner, "trace": trace}
@@ -204,15 +230,16 @@ class BatchIK:
         self.launches += 1
         return T, Y
 
-    def check_limits(self, Y, tol=1e-6):
-        """Intended-semantics check_distance_limits on the device: violations per problem."""
+    def check_limits(self, Y, tol=1e-6, status=None):
+        """Intended-semantics check_distance_limits on the device: violations per problem.  `status` (int32[B],
+        optional) gets GIK_STATUS_LIMITS (3) where a limit is broken."""
         N = self.plan.N
         Y = self._f64(Y).reshape(-1, N, 3)
         B = Y.shape[0]
         out = self._empty(B, dtype=self.torch.int32)
         with self.torch.cuda.device(self.device):
-            _lib.check(self.lib.gik_check_limits(self.plan.handle, _p(Y), float(tol), B, _p(out), self._stream()),
-                       "gik_check_limits")
+            _lib.check(self.lib.gik_check_limits(self.plan.handle, _p(Y), float(tol), B, _p(out), _p(status),
+                                                 self._stream()), "gik_check_limits")
         self.launches += 1
         return out
 
@@ -227,7 +254,7 @@ class BatchIK:
         if Y_init is None:
             Y_init = self.initialization(g2)
         out = self.solve_points(g2, Y_init, trace_rows=trace_rows)
-        out["goal_d2"] = g2
+        out["goal_d2"], out["T_goal"], out["Y_init"] = g2, T, self._f64(Y_init).reshape(-1, self.plan.N, 3)
         out["q"] = self.joints(out["x"], T)
         if check:
             T_sol, Y_real = self.fk(out["q"], want_points=True)

@@ -61,8 +61,10 @@ class Plan:
         d.n_nodes = int(arrays["n_nodes"])
         d.n_terms = len(arrays["term_i"])
         for key in ("term_i", "term_j", "term_kind", "term_target", "term_goal", "anchor_node", "anchor_pos",
-                    "bs_lower", "bs_upper", "goal_edge_i", "goal_edge_j", "goal_edge_slot", "omega", "T0"):
+                    "bs_lower", "bs_upper", "goal_edge_i", "goal_edge_j", "goal_edge_slot", "omega", "T0",
+                    "limit_i", "limit_j", "limit_lower", "limit_upper"):
             setattr(d, key, ptr(key))
+        d.n_limits = len(arrays["limit_i"]) if arrays.get("limit_i") is not None else 0
         d.n_goal = int(arrays.get("n_goal", 0))
         d.n_anchor = len(arrays["anchor_node"]) if arrays.get("anchor_node") is not None else 0
         d.goal_p = int(arrays.get("goal_p", -1))
@@ -118,7 +120,15 @@ class Plan:
             bs_upper[i, j] = bs_upper[j, i] = np.inf
         np.fill_diagonal(bs_lower, 0.0)
         np.fill_diagonal(bs_upper, 0.0)
+        # check_distance_limits (graph_base.py:219-260, intended semantics): every BELOW / ABOVE edge with the graph's
+        # own bounds -- NOT the bound-smoothing tables above, where goal edges lose their static limits
+        li, lj = np.nonzero(np.triu(graph.below | graph.above, 1))
+        lim_lo = np.where(np.isnan(graph.lower[li, lj]), 0.0, graph.lower[li, lj])
+        lim_up = np.where(np.isnan(graph.upper[li, lj]), np.inf, graph.upper[li, lj])
         return {
+            "limit_i": li.astype(np.int32), "limit_j": lj.astype(np.int32),
+            "limit_lower": np.ascontiguousarray(lim_lo, dtype=np.float64),
+            "limit_upper": np.ascontiguousarray(lim_up, dtype=np.float64),
             "n_nodes": N, "term_i": ti, "term_j": tj, "term_kind": tk, "term_target": tt, "term_goal": tg,
             "n_goal": 2 * A, "anchor_node": anchors,
             "anchor_pos": np.ascontiguousarray(graph.pos[anchors], dtype=np.float64),

@@ -115,6 +115,25 @@ class RiemannianSolver:
         return out
 
 
+    def stream(self, **kw):
+        """Throughput mode: an `IKStream` (graphik_b200/pipeline.py) over this solver's engine -- batches are
+        submitted asynchronously, their small kernels overlap other batches' trust-region launches and goals
+        that need many more iterations than the rest finish in the shadow of later batches.
+        Keywords: slots, inner_budget, carry_capacity, to_host."""
+        from graphik_b200.pipeline import IKStream
+        eng = self.engine
+        eng.opts = self.opts
+        return IKStream(eng, **kw)
+
+    def solve_batches(self, batches, **kw):
+        """solve_batch for a sequence of T_goals arrays / tensors through one IKStream; returns the list of
+        result dicts (device tensors), complete."""
+        st = self.stream(**kw)
+        tickets = [st.submit(T) for T in batches]
+        st.drain()
+        return [st.result(t) for t in tickets]
+
+
 def solve_with_riemannian(graph, T_goal, use_jit=True, jit=None, limit_semantics="reference"):
     """riemannian_solver.py:220-234: (q_sol dict, points[N,3]) or (None, None).
 

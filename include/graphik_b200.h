@@ -16,9 +16,11 @@
  *     caller (e.g. torch tensors); the library allocates only inside
  *     gik_plan_create.  All floating-point data is IEEE double, row-major.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls
- *     are asynchronous on that stream.  A plan is immutable after creation and
- *     may be shared between streams; it belongs to the device that was current
- *     when it was created.
+ *     are asynchronous on that stream.  A plan is immutable after creation, owns
+ *     no scratch memory and may be shared between streams and threads (per-call
+ *     scratch -- work_counter, workspace, carry queues -- is the caller's, one per
+ *     concurrently running call); it belongs to the device that was current when
+ *     it was created.
  *   - Point sets are Y[B][N][3]; node order is the ProblemGraph's node order
  *     (p0, x, y, q0, p1, q1, ..., pn, qn, obstacles...).
  */
@@ -45,6 +47,10 @@ extern "C" {
 #define GIK_STATUS_CONVERGED 0   /* gradnorm < mingradnorm            */
 #define GIK_STATUS_MAXITER 1     /* outer iterations reached maxiter  */
 #define GIK_STATUS_NAN 2         /* non-finite cost at the start      */
+#define GIK_STATUS_LIMITS 3      /* solved, but a distance limit is broken after joint recovery (set by
+                                    gik_check_limits when asked to; riemannian_solver.py:230-232)     */
+#define GIK_STATUS_PENDING 4     /* parked by gik_rtr_solve_sliced: final values arrive with a later launch */
+#define GIK_STATUS_MAXTIME 5     /* wall time since the problem started reached maxtime               */
 
 typedef struct GikPlan GikPlan;
 
@@ -85,6 +91,14 @@ typedef struct {
     /* joint recovery (graph_revolute.py:251-318) */
     int32_t n_joints;           /* 0: tables absent */
     const double *T0;           /* [(n_joints+1)][4][4] zero-configuration frames */
+    /* check_distance_limits (graph_base.py:219-260): the edges carrying a BELOW / ABOVE limit with
+     * their unsquared bounds, independent of the goal (an edge that is also a goal edge keeps its
+     * limit here although bound smoothing uses the goal's exact distance for it) */
+    int32_t n_limits;
+    const int32_t *limit_i;     /* [n_limits] */
+    const int32_t *limit_j;
+    const double *limit_lower;  /* [n_limits]; no lower limit: 0    */
+    const double *limit_upper;  /* [n_limits]; no upper limit: +inf */
 } GikPlanDesc;
 
 /* Options of the trust-region solve; defaults = riemannian_solver.py:44-50 over
@@ -101,15 +115,19 @@ typedef struct {
     double Delta_bar;           /* 13 = typicaldist = 10 + k */
     double Delta0;              /* Delta_bar / 8 */
     int32_t kernel;             /* GIK_KERNEL_*: which implementation gik_rtr_solve launches (same results) */
+    double maxtime;             /* 1000 s (pymanopt Solver default, tested first at the end of every outer
+                                   iteration, then maxiter, then mingradnorm); <= 0: no time limit */
 } GikSolveOpts;
 
 /* gik_rtr_solve implementations (identical algorithm, different mapping to the SM) */
-#define GIK_KERNEL_AUTO 0        /* N <= 32: latency kernel, throughput kernel for B >= 49152;
+#define GIK_KERNEL_AUTO 0        /* N <= 16: two problems per warp for batches > 32768 and for the bulk launches of
+                                    gik_rtr_solve_sliced, one warp per problem otherwise (same bits either way);
+                                    N <= 32: one warp per problem;
                                     N > 32: dense kernel when >= 1/8 of the node pairs carry a term (and no pair
                                     carries two), else the two-nodes-per-lane warp kernel (N <= 64), else generic */
 #define GIK_KERNEL_LATENCY 1     /* one warp per problem: register slot cache (N <= 32), two nodes per lane with a
                                     shared-memory slot cache (32 < N <= 64) */
-#define GIK_KERNEL_THROUGHPUT 2  /* two problems per warp in lock-step (N <= 16) */
+#define GIK_KERNEL_THROUGHPUT 2  /* two problems per warp (N <= 16); bit-identical to GIK_KERNEL_LATENCY */
 #define GIK_KERNEL_GENERIC 3     /* W-lane groups, any N <= 128 */
 #define GIK_KERNEL_DENSE 4       /* one CTA per problem, two CTAs per SM, packed symmetric pair cache in shared
                                     memory (32 < N <= 128) */
@@ -147,19 +165,24 @@ int gik_hessvec(const GikPlan *plan, const double *Y, const double *W, const dou
  * out[B][N][3] = Z - Y * Omega,  Omega X + X Omega = Y^T Z - Z^T Y. */
 int gik_proj(int32_t N, const double *Y, const double *Z, int32_t B, double *out, void *stream);
 
+/* Per-call device workspace of gik_bounds / gik_init / gik_bounds_init in bytes: 0 for N <= 96 (everything
+ * stays in shared memory; pass NULL), else the spilled N x N matrices of the resident CTAs.  The plan owns no
+ * scratch memory: calls that may run concurrently (different streams) need one workspace each. */
+int64_t gik_workspace_bytes(const GikPlan *plan);
+
 /* bound_smoothing (dgp.py:192-231) for B goals: lb, ub [B][N][N] (unsquared). */
 int gik_bounds(const GikPlan *plan, const double *goal_d2, int32_t B, double *lb, double *ub,
-               void *stream);
+               void *workspace, void *stream);
 
 /* RiemannianSolver.generate_initialization (riemannian_solver.py:67-75; dgp.py:28-31,
  * 150-183) from bounds: lb, ub [B][N][N] -> Y_init[B][N][3]. */
 int gik_init(const GikPlan *plan, const double *lb, const double *ub, int32_t B, double *Y_init,
-             void *stream);
+             void *workspace, void *stream);
 
 /* bound_smoothing + generate_initialization fused (bounds never leave the SM):
  * goal_d2[B][n_goal] -> Y_init[B][N][3]. */
 int gik_bounds_init(const GikPlan *plan, const double *goal_d2, int32_t B, double *Y_init,
-                    void *stream);
+                    void *workspace, void *stream);
 
 /* TrustRegions.solve + _truncated_conjugate_gradient on PSDFixedRank(N, 3)
  * (trust_region.py:112-599; fixed_rank_psd_sym.py; riemannian_solver.py:178-218)
@@ -175,6 +198,32 @@ int gik_rtr_solve(const GikPlan *plan, const double *goal_d2, const double *Y_in
                   int32_t *iters, int32_t *status, int32_t *n_inner, double *trace,
                   int32_t trace_rows, int32_t *work_counter, void *stream);
 
+/* ---- Deferred stragglers -------------------------------------------------------------------------
+ * The number of tCG iterations a goal needs spans two orders of magnitude (UR10: median 5 k, 0.4 % of the
+ * goals run into maxiter = 3000 with ~240 k), and gik_rtr_solve returns with its slowest problem.
+ * gik_rtr_solve_sliced bounds a launch instead: a problem that has spent `inner_budget` tCG iterations in
+ * this launch PARKS at the next outer-iteration boundary of trust_region.py:179-422 -- its state goes to
+ * an entry of `carry_out` together with the addresses of its outputs, its status reads
+ * GIK_STATUS_PENDING -- and the next call that receives that buffer as `carry_in` resumes it before it
+ * starts any new problem, writing the final values to the ORIGINAL output locations (which the caller
+ * must keep alive).  A parked problem follows bit for bit the trajectory of an unparked one.
+ *   inner_budget <= 0 or carry_out == NULL: nothing parks (a call with carry_in only drains the queue).
+ *   pending (may be NULL): device int32, += 1 for each of this call's problems that parks; the call that
+ *       finishes a parked problem does -= 1 on the address that problem was parked with -- one counter
+ *       per batch tells when the batch is complete.
+ *   B == 0 with carry_in: only resumes.  The two buffers must differ; use them alternately.
+ *   One queue must always be used with the same plan; GIK_KERNEL_LATENCY and GIK_KERNEL_THROUGHPUT may
+ *   alternate on it (identical arithmetic), the other kernels may not be mixed with them.
+ * gik_carry_bytes: size of a queue for `capacity` parked problems; gik_carry_init: format it once
+ * (16-byte aligned device memory).  When the outgoing queue is full, problems simply run on. */
+int64_t gik_carry_bytes(const GikPlan *plan, int32_t capacity);
+int gik_carry_init(const GikPlan *plan, void *carry, int32_t capacity, void *stream);
+int gik_rtr_solve_sliced(const GikPlan *plan, const double *goal_d2, const double *Y_init, int32_t B,
+                         const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
+                         int32_t *iters, int32_t *status, int32_t *n_inner, int32_t inner_budget,
+                         const void *carry_in, void *carry_out, int32_t *pending,
+                         int32_t *work_counter, void *stream);
+
 /* ProblemGraphRevolute.joint_variables (graph_revolute.py:251-318):
  * Y[B][N][3] (+ T_goal[B][4][4] or NULL) -> q[B][n_joints]. */
 int gik_joints(const GikPlan *plan, const double *Y, const double *T_goal, int32_t B, double *q,
@@ -186,11 +235,13 @@ int gik_joints(const GikPlan *plan, const double *Y, const double *T_goal, int32
 int gik_fk(const GikPlan *plan, const double *q, int32_t B, double *T_ee, double *Y, void *stream);
 
 /* ProblemGraph.check_distance_limits (graph_base.py:219-260) with the INTENDED semantics: for every
- * edge carrying a BELOW/ABOVE limit count the realised distances outside [LOWER - tol, UPPER + tol].
- * (As shipped, the reference's own node-type test never fires on revolute graphs, so it reports no
- * violation at all; callers wanting that behaviour simply skip this call.)  Y[B][N][3] -> n_broken[B]. */
+ * edge carrying a BELOW/ABOVE limit (GikPlanDesc.limit_*) count the realised distances outside
+ * [LOWER - tol, UPPER + tol].  (As shipped, the reference's own node-type test never fires on revolute
+ * graphs, so it reports no violation at all; callers wanting that behaviour simply skip this call.)
+ * Y[B][N][3] -> n_broken[B]; status (may be NULL): status[b] = GIK_STATUS_LIMITS where n_broken[b] > 0 and
+ * the solve itself had ended normally (converged or maxiter) -- the (None, None) of riemannian_solver.py:230-232. */
 int gik_check_limits(const GikPlan *plan, const double *Y, double tol, int32_t B, int32_t *n_broken,
-                     void *stream);
+                     int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

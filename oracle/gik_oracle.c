@@ -20,6 +20,7 @@
  * build of costs.py operation for operation.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -466,9 +467,12 @@ void orc_rtr_solve_batch(int B, int N, int E, const int64_t *ii, const int64_t *
                          const double *D /*[B,N,N]*/, const double *omega, const double *psiL,
                          const double *psiU, const orc_params *q, const double *Y_init /*[B,N,3]*/,
                          double *Y_out, double *f, double *gradnorm, int *iters, int *status,
-                         long *n_hess)
+                         long *n_hess, int threads)
 {
-#pragma omp parallel for schedule(dynamic, 1)
+    /* the thread count is set here, not through OMP_NUM_THREADS: libgomp reads the environment once when it is
+     * loaded, and torchrun exports OMP_NUM_THREADS=1 to every rank */
+    if (threads < 1) threads = omp_get_num_procs();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
     for (int b = 0; b < B; ++b) {
         orc_problem p = {N, E, ii, jj, D + (size_t)b * N * N, omega, psiL, psiU};
         iters[b] = orc_rtr_solve(&p, q, Y_init + (size_t)b * N * DIM, Y_out + (size_t)b * N * DIM,

@@ -151,14 +151,12 @@ def proj(Y, Z):
 
 
 def solve_batch(D, omega, psi_L, psi_U, Y_init, params=None, threads=None):
-    """B problems sharing omega/psi (goal-independent), OpenMP over problems."""
+    """B problems sharing omega/psi (goal-independent), OpenMP over problems (`threads`: 0 / None = all cores)."""
     D, Y_init = _f64(D), _f64(Y_init)
     B, N = D.shape[0], D.shape[1]
     proto = Problem(D[0], omega, psi_L, psi_U, True)
     q = default_params(params)
     q.use_limits = 1
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
     Y = np.empty_like(Y_init)
     f, gn = np.empty(B), np.empty(B)
     iters, status = np.empty(B, np.int32), np.empty(B, np.int32)
@@ -168,7 +166,7 @@ def solve_batch(D, omega, psi_L, psi_U, Y_init, params=None, threads=None):
         proto.ii.ctypes.data_as(_c_i64_p), proto.jj.ctypes.data_as(_c_i64_p), _dp(D),
         _dp(proto.omega), _dp(proto.psiL), _dp(proto.psiU), ctypes.byref(q), _dp(Y_init), _dp(Y),
         _dp(f), _dp(gn), iters.ctypes.data_as(_c_int_p), status.ctypes.data_as(_c_int_p),
-        nh.ctypes.data_as(_c_long_p))
+        nh.ctypes.data_as(_c_long_p), ctypes.c_int(int(threads or 0)))
     return {"x": Y, "f(x)": f, "gradnorm": gn, "iterations": iters, "status": status, "n_hess": nh}
 
 

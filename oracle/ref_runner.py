@@ -25,21 +25,49 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REFERENCE = os.environ.get("GRAPHIK_REFERENCE", "/root/reference")
 REF_BUILD = os.path.join(HERE, "_ref")
+
+
+def _default_reference():
+    """The read-only tree in the build container; on the GPU box the copy `oracle.ref_arm.install()` made."""
+    for cand in (os.environ.get("GRAPHIK_REFERENCE"), "/root/reference", os.path.join(REF_BUILD, "reference")):
+        if cand and os.path.isdir(os.path.join(cand, "graphik")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE = _default_reference()
 
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE, "graphik"))
 
 
+def costgrd_dir():
+    """numba.pycc emits code for the CPU it runs on: one build per CPU model (the build container's and the
+    GPU box's hosts differ, and oracle/_ref/ travels between them)."""
+    import hashlib
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("model name", "flags")):
+                    model += line
+                    if line.startswith("flags"):
+                        break
+    except OSError:
+        pass
+    return os.path.join(REF_BUILD, "costgrd_" + hashlib.sha1(model.encode()).hexdigest()[:10])
+
+
 def _build_costgrd():
     """numba.pycc AOT build of the reference's costs.py (costs.py:208-209)."""
-    os.makedirs(REF_BUILD, exist_ok=True)
-    for f in os.listdir(REF_BUILD):
+    out_dir = costgrd_dir()
+    os.makedirs(out_dir, exist_ok=True)
+    for f in os.listdir(out_dir):
         if f.startswith("costgrd") and f.endswith(".so"):
             return
-    scratch = os.path.join(REF_BUILD, "costgrd_build")
+    scratch = os.path.join(out_dir, "build")
     os.makedirs(scratch, exist_ok=True)
     # numba.pycc compiles the module it is handed; it must be run from a
     # writable directory, and the reference tree is read-only.  The copy is a
@@ -52,7 +80,7 @@ def _build_costgrd():
                    stderr=subprocess.DEVNULL)
     for f in os.listdir(scratch):
         if f.startswith("costgrd") and f.endswith(".so"):
-            shutil.move(os.path.join(scratch, f), os.path.join(REF_BUILD, f))
+            shutil.move(os.path.join(scratch, f), os.path.join(out_dir, f))
     shutil.rmtree(scratch, ignore_errors=True)
 
 
@@ -89,8 +117,8 @@ def load_reference(with_costgrd=True):
 
     if with_costgrd:
         _build_costgrd()
-        if REF_BUILD not in sys.path:
-            sys.path.insert(0, REF_BUILD)
+        if costgrd_dir() not in sys.path:
+            sys.path.insert(0, costgrd_dir())
         costgrd = importlib.import_module("costgrd")
         sys.modules["graphik.solvers.costgrd"] = costgrd
 

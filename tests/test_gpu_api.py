@@ -120,12 +120,15 @@ def test_c_abi_error_codes_and_empty_batches():
     assert L.gik_cost_grad(h, null, null, 0, null, null, null) == 0
     assert L.gik_hessvec(h, null, null, null, 0, null, null) == 0
     assert L.gik_proj(16, null, null, 0, null, null) == 0
-    assert L.gik_bounds(h, null, 0, null, null, null) == 0
-    assert L.gik_init(h, null, null, 0, null, null) == 0
-    assert L.gik_bounds_init(h, null, 0, null, null) == 0
+    assert L.gik_bounds(h, null, 0, null, null, null, null) == 0
+    assert L.gik_init(h, null, null, 0, null, null, null) == 0
+    assert L.gik_bounds_init(h, null, 0, null, null, null) == 0
     assert L.gik_joints(h, null, null, 0, null, null) == 0
     assert L.gik_fk(h, null, 0, null, null, null) == 0
-    assert L.gik_check_limits(h, null, 1e-6, 0, null, null) == 0
+    assert L.gik_check_limits(h, null, 1e-6, 0, null, null, null) == 0
+    assert L.gik_rtr_solve_sliced(h, null, null, 0, None, null, null, null, null, null, null, 0, null, null, null,
+                                  null, null) == 0
+    assert L.gik_workspace_bytes(h) == 0 and L.gik_carry_bytes(h, 10) == 16 + 10 * 8 * (22 + 6 * 16)
     assert L.gik_rtr_solve(h, null, null, 0, None, null, null, null, null, null, null, null, 0, null, null) == 0
     # null pointers with B > 0 -> GIK_EINVAL (-1) and a message
     assert L.gik_cost_grad(h, null, null, 4, null, null, null) == -1

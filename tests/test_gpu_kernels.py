@@ -170,3 +170,31 @@ def test_check_limits_device_vs_host_intended():
     assert np.array_equal(dev, host)
     assert dev.max() > 0 and (dev == 0).any()
     assert all(len(graph.check_distance_limits(Y[k].cpu().numpy(), tol=1e-6)) == 0 for k in range(5))  # as shipped
+
+
+def test_check_limits_obstacle_on_goal_edge_and_status_code():
+    """Intended obstacle semantics: the pair (p_n, obstacle) is a GOAL edge for bound smoothing (exact distance per
+    goal) and still carries the obstacle's lower limit for check_distance_limits.  A realisation whose end-effector
+    point lies inside an obstacle sphere must be reported by the device check exactly as by the host one, and
+    `status` becomes GIK_STATUS_LIMITS (3) for those goals only."""
+    import numpy as np
+    import torch
+    from graphik_b200.engine import BatchIK
+    robot, graph = load_robot("kuka", graph_params={"obstacle_semantics": "intended"})
+    rng = np.random.RandomState(4)
+    Q = -np.pi + 2 * np.pi * rng.rand(64, robot.n)
+    P = robot.fk_all(Q)[:, robot.n, :3, 3]
+    # spheres centred on the end-effector points of the first goals: those goals end inside an obstacle
+    for k in range(3):
+        graph.add_spherical_obstacle("o%d" % k, P[k] + np.array([0.0, 0.0, 0.01]), 0.25)
+    eng = BatchIK(graph)
+    T, Y = eng.fk(Q)
+    status = torch.zeros(64, dtype=torch.int32, device=Y.device)
+    status[10] = 2                                    # a NaN start keeps its own code
+    dev = eng.check_limits(Y, tol=1e-6, status=status).cpu().numpy()
+    host = np.array([len(graph.check_distance_limits(Y[k].cpu().numpy(), tol=1e-6, semantics="intended"))
+                     for k in range(64)])
+    assert np.array_equal(dev, host)
+    assert (dev[:3] > 0).all()
+    st = status.cpu().numpy()
+    assert np.array_equal(st == 3, (dev > 0) & (np.arange(64) != 10)) and st[10] == 2
