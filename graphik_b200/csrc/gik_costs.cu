@@ -87,6 +87,7 @@ k_costs(PlanView pv, const double *__restrict__ Y, const double *__restrict__ Wd
     for (int b = blockIdx.x * GPB + gid; b < B; b += gridDim.x * GPB) {
         double x[NPL][3], w[NPL][3], r[NPL][3];
         load_points<W, NPL>(Y + (size_t)b * stride, pv.N, lane, x);
+        __syncwarp(c.mask);   // the group has finished reading the previous problem's buffers
         for (int k = lane; k < pv.n_goal; k += W) goal[k] = goal_d2[(size_t)b * pv.n_goal + k];
         gik_publish<W, NPL>(c.P, x, lane);
         if (MODE == 1) {

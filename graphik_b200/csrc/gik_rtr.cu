@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
                 int j = 0;
                 for (j = 0; j < o.maxinner; ++j) {
                     // Hdelta = proj(x, lhess(x, delta))
+                    __syncwarp(mask);   // every lane has read the previous direction out of V
                     gik_publish<W, NPL>(c.V, dl, lane);
                     __syncwarp(mask);
                     gik_pass_hess<W, NPL>(c, x, dl, Hd);
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
                 for (int m = 0; m < NPL; ++m)
 #pragma unroll
                     for (int q = 0; q < 3; ++q) dl[m][q] = x[m][q] + eta[m][q];
+                __syncwarp(mask);       // every lane has finished the edge passes that read P
                 gik_publish<W, NPL>(c.P, dl, lane);
                 __syncwarp(mask);
                 double v[10];
@@ -357,10 +359,10 @@ __global__ void __launch_bounds__(kThreads) k_rtr(const RtrArgs a)
                 if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
                 if (may_park && inner_total - inner_entry >= a.inner_budget) {
-                    if (lane == 0) park_slot = gik_carry_reserve(a.carry_out);
+                    if (lane == 0) park_slot = gik_try_park(a, n_res + a.B);
                     park_slot = __shfl_sync(mask, park_slot, leader, 32);
                     if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
-                    may_park = false;   // queue full: run this problem to its end
+                    if (park_slot == -1) may_park = false;   // queue full: run this problem to its end
                 }
             }
         }

@@ -71,6 +71,18 @@ __device__ __forceinline__ int gik_carry_reserve(char *q)
     atomicAdd(&h->full, 1);
     return -1;
 }
+// Park decision of one problem, taken by ONE thread of its group at an outer-iteration boundary once the problem has
+// spent its budget in this launch: it parks only when the launch has no new work left to hand out (the work counter
+// has passed the last item).  Until then a long problem keeps its warp -- the other warps pull the new problems --
+// so it advances without interruption for as long as the launch has a reason to live; once the queue is dry it
+// leaves within one outer iteration and the launch ends with its work, not with its slowest problem.
+// Returns the reserved entry (>= 0), -1: queue full (never try again), -2: not now.
+__device__ __forceinline__ int gik_try_park(const RtrArgs &a, int n_items)
+{
+    if (*reinterpret_cast<volatile int32_t *>(a.work_counter) < n_items) return -2;
+    return gik_carry_reserve(a.carry_out);
+}
+
 __device__ __forceinline__ double *gik_carry_slot(char *q, int slot)
 {
     const GikCarryHdr *h = reinterpret_cast<const GikCarryHdr *>(q);

@@ -586,11 +586,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
                 if (may_park && inner_total - inner_entry >= a.inner_budget) {
                     __syncthreads();
-                    if (tid == 0) s_b[1] = gik_carry_reserve(a.carry_out);
+                    if (tid == 0) s_b[1] = gik_try_park(a, n_res + a.B);
                     __syncthreads();
                     park_slot = s_b[1];
                     if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
-                    may_park = false;   // queue full: run this problem to its end
+                    if (park_slot == -1) may_park = false;   // queue full: run this problem to its end
                 }
             }
         }

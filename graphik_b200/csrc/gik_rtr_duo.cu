@@ -60,10 +60,20 @@ __host__ __device__ constexpr int duo_smem_doubles(int SPL, int goal_pad)
     return 192 + 2 * goal_pad + SPL * 32 + SPL * 128 + 4 * kRS + 8 + 2;
 }
 
+// Where the slot cache lives.  Measured on UR10 (SPL = 9, 65536 goals, maxiter 300): 12 warps / SM with the cache in
+// shared memory and 8 warps / SM (248 registers) run at the same 2.11 G tCG iterations / s -- the shared-memory pipe is
+// the common limit (168 wavefronts per trip, 43 % of them cache reads) -- so up to 9 slots the cache moves into the
+// registers that 8 warps / SM leave free.
+#ifndef GIK_DUO_REGCACHE
+#define GIK_DUO_REGCACHE 1
+#endif
+__host__ __device__ constexpr bool duo_cache_in_regs(int SPL) { return GIK_DUO_REGCACHE && SPL <= 9; }
+
 template <int SPL>
-__global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const uint32_t *__restrict__ duo_info,
+__global__ void __launch_bounds__(kThreads, duo_cache_in_regs(SPL) ? 8 : 12) k_rtr_duo(const RtrArgs a, const uint32_t *__restrict__ duo_info,
                                                           const double *__restrict__ duo_target)
 {
+    constexpr bool RC = duo_cache_in_regs(SPL);
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int node = lane & 15;
@@ -116,6 +126,11 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
 
     double x[3] = {0, 0, 0}, g[3] = {0, 0, 0}, eta[3] = {0, 0, 0}, Heta[3] = {0, 0, 0}, r[3] = {0, 0, 0},
            dl[3] = {0, 0, 0}, Hd[3];
+    double sc[RC ? SPL : 1][4];   // slot cache in registers: 2 act (x_i - x_j), 2 act (d_ij - T_ij)
+    if (RC) {
+#pragma unroll
+        for (int s = 0; s < (RC ? SPL : 1); ++s) { sc[s][0] = 0.0; sc[s][1] = 0.0; sc[s][2] = 0.0; sc[s][3] = 0.0; }
+    }
     double fx = 0, gg = 0, norm_grad = 0, Mi[6] = {0, 0, 0, 0, 0, 0}, sg[3] = {0, 0, 0}, u[3] = {0, 0, 0}, Delta = 0;
     double e_Pe = 0, z_r = 1, inv_z_r = 1, d_Pd = 1, e_Pd = 0, model_value = 0;
     trm::TcgStart ts = {0, 0, 0, 1};
@@ -139,8 +154,13 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
             const double dx = trm::sub(p[0], gik_lds<PO>(vj[s])), dy = trm::sub(p[1], gik_lds<PO + CS>(vj[s])),
                          dz = trm::sub(p[2], gik_lds<PO + 2 * CS>(vj[s]));
             const trm::SlotEval e = trm::slot_cost(dx, dy, dz, tgt[s * 32], kind, fpart[s & 1], gacc[s & 1]);
-            scm[(s * 2 + 0) * 32] = make_double2(trm::mul(e.two, dx), trm::mul(e.two, dy));
-            scm[(s * 2 + 1) * 32] = make_double2(trm::mul(e.two, dz), trm::mul(2.0, e.rr));
+            if (RC) {
+                sc[RC ? s : 0][0] = trm::mul(e.two, dx); sc[RC ? s : 0][1] = trm::mul(e.two, dy);
+                sc[RC ? s : 0][2] = trm::mul(e.two, dz); sc[RC ? s : 0][3] = trm::mul(2.0, e.rr);
+            } else {
+                scm[(s * 2 + 0) * 32] = make_double2(trm::mul(e.two, dx), trm::mul(e.two, dy));
+                scm[(s * 2 + 1) * 32] = make_double2(trm::mul(e.two, dz), trm::mul(2.0, e.rr));
+            }
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) gout[q] = trm::add(trm::mul(2.0, gacc[0][q]), trm::mul(2.0, gacc[1][q]));
@@ -328,9 +348,9 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
                 } else {
                     int park_slot = -1;
                     if (may_park && inner_total - inner_entry >= a.inner_budget) {
-                        if (node == 0) park_slot = gik_carry_reserve(a.carry_out);
+                        if (node == 0) park_slot = gik_try_park(a, n_res + a.B);
                         park_slot = __shfl_sync(gmask, park_slot, hbase, 32);
-                        if (park_slot < 0) may_park = false;   // queue full: run this problem to its end
+                        if (park_slot == -1) may_park = false;   // queue full: run this problem to its end
                     }
                     if (park_slot >= 0) {
                         status = GIK_STATUS_PENDING;
@@ -353,8 +373,13 @@ __global__ void __launch_bounds__(kThreads, 12) k_rtr_duo(const RtrArgs a, const
         for (int s = 0; s < SPL; ++s) {
             const double wx = trm::sub(dl[0], gik_lds<0>(vj[s])), wy = trm::sub(dl[1], gik_lds<CS>(vj[s])),
                          wz = trm::sub(dl[2], gik_lds<2 * CS>(vj[s]));
-            const double2 a0 = scm[(s * 2 + 0) * 32], a1 = scm[(s * 2 + 1) * 32];
-            trm::slot_hess(a0.x, a0.y, a1.x, a1.y, wx, wy, wz, z[s & 1], zb[s & 1]);
+            if (RC) {
+                trm::slot_hess(sc[RC ? s : 0][0], sc[RC ? s : 0][1], sc[RC ? s : 0][2], sc[RC ? s : 0][3], wx, wy, wz,
+                               z[s & 1], zb[s & 1]);
+            } else {
+                const double2 a0 = scm[(s * 2 + 0) * 32], a1 = scm[(s * 2 + 1) * 32];
+                trm::slot_hess(a0.x, a0.y, a1.x, a1.y, wx, wy, wz, z[s & 1], zb[s & 1]);
+            }
         }
         double Z[3];
 #pragma unroll

@@ -41,12 +41,14 @@ __host__ __device__ constexpr int fast_smem_doubles(int LPN, int SPL, bool SMC, 
     return 6 * (32 / LPN) + goal_pad + SPL * 32 + (SMC ? SPL * 128 : 0) + 8 * gik_red_stride(32 / LPN) + 8 + 2;
 }
 
-// LAT: latency variant (butterflies, same bits as the shared-memory reduction of the throughput variant)
 template <int LPN, int K, bool LAT>
 __device__ __forceinline__ void fast_allreduce(double (&v)[K], const GikRedAddr &ra, int lane)
 {
-    if (LAT) node_allreduce_b<LPN, K>(v);
-    else node_allreduce_s<LPN, K>(v, ra);
+
+    // measured on UR10 (one 4096-goal batch, i.e. the slowest goal alone on its SM): the shared-memory reduction
+    // beats xor butterflies in the latency variant as well (140.6 vs 148.7 ms) -- shuffles and shared-memory accesses
+    // issue at one per ~4.4 cycles per scheduler, and the butterfly needs 64 of them against 26
+    node_allreduce_s<LPN, K>(v, ra);
 }
 
 // SMC: keep the slot cache in shared memory ([slot][2][lane] double2, conflict-free) instead of registers --
@@ -335,10 +337,10 @@ __device__ __forceinline__ void rtr_fast_body(const RtrArgs &a, const uint32_t *
                 if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
                 if (may_park && inner_total - inner_entry >= a.inner_budget) {
-                    if (lane == 0) park_slot = gik_carry_reserve(a.carry_out);
+                    if (lane == 0) park_slot = gik_try_park(a, n_res + a.B);
                     park_slot = __shfl_sync(GIK_FULL_MASK, park_slot, 0, 32);
                     if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
-                    may_park = false;   // queue full: run this problem to its end
+                    if (park_slot == -1) may_park = false;   // queue full: run this problem to its end
                 }
             }
         }
@@ -380,8 +382,8 @@ __host__ __device__ constexpr int fast_min_blocks(int LPN, int SPL) { return (LP
 // LAT = false: throughput variant (as many warps per SM as the registers allow, shared-memory reductions).
 // LAT = true: latency variant for launches with few problems -- small batches and the draining launches of
 // gik_rtr_solve_sliced, where the wall time is the dependency chain of the slowest problems: 8 warps / SM (255
-// registers: no rematerialised addresses, more loads in flight) and butterfly reductions.  Both variants compile the
-// same arithmetic in the same order and give bit-identical results.
+// registers: no rematerialised addresses, more loads in flight).  Both variants compile the same explicitly rounded
+// arithmetic (gik_tr_math.cuh) and give bit-identical results.
 template <int LPN, int SPL, bool LAT>
 __global__ void __launch_bounds__(kThreads, LAT ? 8 : fast_min_blocks(LPN, SPL))
 k_rtr_fast(const RtrArgs a, const uint32_t *__restrict__ fast_info, const double *__restrict__ fast_target)
@@ -760,10 +762,10 @@ __device__ __forceinline__ void rtr_fast2_body(const RtrArgs &a, const uint32_t 
                 if (k_outer >= o.maxiter) { status = GIK_STATUS_MAXITER; break; }
                 if (norm_grad < o.mingradnorm) { status = GIK_STATUS_CONVERGED; break; }
                 if (may_park && inner_total - inner_entry >= a.inner_budget) {
-                    if (lane == 0) park_slot = gik_carry_reserve(a.carry_out);
+                    if (lane == 0) park_slot = gik_try_park(a, n_res + a.B);
                     park_slot = __shfl_sync(GIK_FULL_MASK, park_slot, 0, 32);
                     if (park_slot >= 0) { status = GIK_STATUS_PENDING; break; }
-                    may_park = false;   // queue full: run this problem to its end
+                    if (park_slot == -1) may_park = false;   // queue full: run this problem to its end
                 }
                 __syncwarp();
             }

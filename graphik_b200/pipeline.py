@@ -73,15 +73,15 @@ class IKStream:
 
     HOST_RING = 8
 
-    def __init__(self, engine: BatchIK, slots=2, inner_budget=None, carry_capacity=None, to_host=False,
+    def __init__(self, engine: BatchIK, slots=1, inner_budget=None, carry_capacity=None, to_host=False,
                  max_outstanding=64, record_events=False):
         self.eng = engine
         self.torch = engine.torch
         self.lib = engine.lib
         N = engine.plan.N
-        # tCG iterations a goal may spend in one launch: about the median goal, so that a launch lasts about as long as
-        # its share of work (measured on UR10, 20 x 4096 goals, 2 slots: 110 k solves/s at 4096, 106 k at 16384)
-        self.inner_budget = int(inner_budget) if inner_budget is not None else 4096
+        # tCG iterations a goal must have spent in a launch before it may park once the launch has no new goal left
+        # (measured on UR10, 20 x 4096 goals, one slot: 144 k solves/s at 512, 140 k at 1024, 136 k at 2048, 119 k at 4096)
+        self.inner_budget = int(inner_budget) if inner_budget is not None else 512
         self.capacity = int(carry_capacity) if carry_capacity is not None else 16384
         self.to_host = bool(to_host)
         self.slots = [_Slot(engine, self.capacity, max_outstanding) for _ in range(max(1, int(slots)))]
@@ -232,6 +232,24 @@ class IKStream:
                 raise _lib.GikError("a drained slot still reports parked goals")
             tk.late = True   # not seen complete before this launch: some of its goals may have arrived with it
             self._finalise(tk)
+
+    def reserve(self, n_batches, B):
+        """Prime torch's caching allocator for `n_batches` outstanding batches of B goals: without it the first pass
+        over a long stream calls cudaMalloc from submit(), and cudaMalloc waits for the running launch."""
+        eng, torch = self.eng, self.torch
+        N, n, ng = eng.plan.N, max(eng.plan.n_joints, 1), max(eng.plan.n_goal, 1)
+        per_slot = -(-int(n_batches) // len(self.slots))
+        with torch.cuda.device(eng.device):
+            for sl in self.slots:
+                with torch.cuda.stream(sl.stream):
+                    hold = []
+                    for _ in range(per_slot):
+                        hold += [eng._empty(B, 4, 4), eng._empty(B, ng), eng._empty(B, N, 3), eng._empty(B, N, 3),
+                                 eng._empty(B), eng._empty(B), eng._empty(B, dtype=torch.int32),
+                                 eng._empty(B, dtype=torch.int32), eng._empty(B, dtype=torch.int32), eng._empty(B, n),
+                                 eng._empty(B, n)]
+                    del hold
+                sl.stream.synchronize()
 
     def drain_slot(self, sl):
         if self._drain_launch(sl):

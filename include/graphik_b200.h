@@ -201,12 +201,14 @@ int gik_rtr_solve(const GikPlan *plan, const double *goal_d2, const double *Y_in
 /* ---- Deferred stragglers -------------------------------------------------------------------------
  * The number of tCG iterations a goal needs spans two orders of magnitude (UR10: median 5 k, 0.4 % of the
  * goals run into maxiter = 3000 with ~240 k), and gik_rtr_solve returns with its slowest problem.
- * gik_rtr_solve_sliced bounds a launch instead: a problem that has spent `inner_budget` tCG iterations in
- * this launch PARKS at the next outer-iteration boundary of trust_region.py:179-422 -- its state goes to
- * an entry of `carry_out` together with the addresses of its outputs, its status reads
- * GIK_STATUS_PENDING -- and the next call that receives that buffer as `carry_in` resumes it before it
- * starts any new problem, writing the final values to the ORIGINAL output locations (which the caller
- * must keep alive).  A parked problem follows bit for bit the trajectory of an unparked one.
+ * gik_rtr_solve_sliced bounds a launch instead: once the launch has handed out its last new problem, every
+ * problem that has spent at least `inner_budget` tCG iterations in it PARKS at its next outer-iteration
+ * boundary of trust_region.py:179-422 -- its state goes to an entry of `carry_out` together with the
+ * addresses of its outputs, its status reads GIK_STATUS_PENDING -- and the next call that receives that
+ * buffer as `carry_in` resumes it before it starts any new problem, writing the final values to the
+ * ORIGINAL output locations (which the caller must keep alive).  So a launch lasts as long as its work,
+ * long problems run without interruption while there is new work around them, and a parked problem
+ * follows bit for bit the trajectory of an unparked one.
  *   inner_budget <= 0 or carry_out == NULL: nothing parks (a call with carry_in only drains the queue).
  *   pending (may be NULL): device int32, += 1 for each of this call's problems that parks; the call that
  *       finishes a parked problem does -= 1 on the address that problem was parked with -- one counter
@@ -242,6 +244,12 @@ int gik_fk(const GikPlan *plan, const double *q, int32_t B, double *T_ee, double
  * the solve itself had ended normally (converged or maxiter) -- the (None, None) of riemannian_solver.py:230-232. */
 int gik_check_limits(const GikPlan *plan, const double *Y, double tol, int32_t B, int32_t *n_broken,
                      int32_t *status, void *stream);
+
+/* CIDGIK, the closed-form Fantope step only: solve_fantope_closed_form (solvers/convex_iteration.py:43-53),
+ * C[b] = U U^T with U the eigenvectors of the n - d smallest eigenvalues of the symmetric G[b][n][n] (n <= 32);
+ * eigvals[B][n] ascending (may be NULL).  The semidefinite programs of the convex iteration (MOSEK through cvxpy,
+ * sdp_snl.py:874-967) are not part of this library. */
+int gik_fantope(int32_t n, int32_t d, const double *G, int32_t B, double *C, double *eigvals, void *stream);
 
 #ifdef __cplusplus
 }

@@ -160,3 +160,31 @@ def test_engine_is_cached_on_the_graph_and_invalidated_by_edits():
     q, Y = solve_with_riemannian(graph, g["T_goal"][1])
     assert graph._gik_engine_cache[1] is not eng1 and Y.shape == (17, 3)
     assert RiemannianSolver(graph).engine is graph._gik_engine_cache[1]
+
+
+def test_fantope_closed_form_vs_numpy():
+    """CIDGIK's closed-form Fantope step (reference convex_iteration.py:43-53) on a batch of Gram matrices of the size
+    the UR10 relaxation has (n + d = 13) and at the kernel's limit (32): against numpy.eigh, which is what the
+    reference calls.  The projector is independent of eigenvector signs, so the comparison is direct."""
+    import torch
+    from graphik_b200.solvers.convex_iteration import (solve_fantope_closed_form, solve_fantope_closed_form_batch,
+                                                       solve_with_cidgik)
+    rng = np.random.default_rng(3)
+    for n, d, B in ((13, 3, 257), (32, 3, 33), (5, 2, 4)):
+        P = rng.normal(size=(B, n, d + 2))
+        G = P @ P.transpose(0, 2, 1) + 1e-3 * np.eye(n)          # near low rank, like an SDP iterate
+        G[0] = np.diag(np.arange(n, dtype=float))                  # already diagonal
+        C, ev = solve_fantope_closed_form_batch(G, d)
+        C, ev = C.cpu().numpy(), ev.cpu().numpy()
+        for b in range(B):
+            w, Q = np.linalg.eigh(G[b])
+            U = np.flip(Q, 1)[:, d:]
+            ref = U @ U.T
+            assert np.max(np.abs(C[b] - ref)) <= 1e-10, (n, b, np.max(np.abs(C[b] - ref)))
+            assert np.max(np.abs(ev[b] - w)) <= 1e-12 * max(1.0, np.max(np.abs(w)))
+        assert np.allclose(np.trace(C, axis1=1, axis2=2), n - d, atol=1e-10)
+        assert np.max(np.abs(C @ C - C)) <= 1e-10                  # a projector
+    C1, seconds = solve_fantope_closed_form(G[1], d)               # the reference's signature
+    assert np.max(np.abs(C1 - C[1])) == 0.0 and seconds >= 0.0
+    with pytest.raises(NotImplementedError):
+        solve_with_cidgik(None, None)

@@ -44,8 +44,9 @@ def test_trace_agrees_with_oracle_on_leading_iterations(name):
         same = np.all(tr[k, :m][:, [1, 2, 4]] == ref[:m][:, [1, 2, 4]], axis=1)
         n_same = m if same.all() else int(np.argmin(same))
         lead.append(n_same)
-        # the first outer iterations must be decision-identical and numerically tight
-        assert n_same >= min(4, m), (name, k, n_same, tr[k, :6], ref[:6])
+        # the first outer iterations must be decision-identical and numerically tight (observed on the 30 golden
+        # goals: 7 .. 46 identical leading iterations before rounding differences flip a decision)
+        assert n_same >= min(7, m), (name, k, n_same, tr[k, :8], ref[:8])
         np.testing.assert_allclose(tr[k, :min(4, m), 3], ref[:min(4, m), 3], rtol=1e-6)
         np.testing.assert_allclose(tr[k, :min(4, m), 0], ref[:min(4, m), 0], rtol=0)  # Delta: exact
     print(name, "decision-identical leading outer iterations per goal:", lead)
