@@ -330,14 +330,21 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         p->last_joint_z_aligned = sqrt(cx * cx + cy * cy) < 1e-10;
     }
 
-    // k_bounds_init works on three N x N fp64 matrices per goal: keep them in shared memory when
-    // they fit (227 KB per CTA), else spill the third / all three to an L2-resident scratch
+    // k_bounds_init works on three N x N fp64 matrices per goal.  It is latency bound, so what counts is the number of
+    // goals in flight per SM: the third matrix (written and read once or twice per goal) moves to an L2-resident
+    // workspace of the caller's when that admits more CTAs per SM (mode 1), and all three do when not even two fit (mode 2)
     {
         const size_t small = (size_t)gik_bi_small_doubles(N) * sizeof(double);
         const size_t mat = (size_t)N * N * sizeof(double);
-        const size_t cap = 227 * 1024;
-        p->bi_mode = small + 3 * mat <= cap ? 0 : (small + 2 * mat <= cap ? 1 : 2);
-        p->bi_blocks = p->bi_mode == 1 ? p->sm_count : 2 * p->sm_count;
+        const size_t cap = 227 * 1024, per_cta = 1024;
+        const int regs = gik_bi_reg_ctas(N);
+        int occ0 = (int)((cap + per_cta) / (small + 3 * mat + per_cta)), occ1 = (int)((cap + per_cta) / (small + 2 * mat + per_cta));
+        if (small + 3 * mat > cap) occ0 = 0;
+        if (small + 2 * mat > cap) occ1 = 0;
+        if (occ0 > regs) occ0 = regs;
+        if (occ1 > regs) occ1 = regs;
+        p->bi_mode = (occ0 >= 1 && occ0 >= occ1) ? 0 : (occ1 >= 1 ? 1 : 2);
+        p->bi_blocks = p->bi_mode == 1 ? p->sm_count * occ1 : 2 * p->sm_count;
     }
 
     bool ok = true;
@@ -363,6 +370,22 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     if (d->bs_lower && d->bs_upper) {
         ok = ok && !upload(&p->bs_lower, d->bs_lower, (size_t)N * N);
         ok = ok && !upload(&p->bs_upper, d->bs_upper, (size_t)N * N);
+        // column lists of the positive lower bounds for the first max-plus product of k_bounds_init; the pairs with
+        // p_n / q_n are patched per goal and handled from two dense rows there
+        const int gp = d->n_goal_edges > 0 ? d->goal_p : -1, gq = d->n_goal_edges > 0 ? d->goal_q : -1;
+        std::vector<int32_t> lptr(N + 1, 0), lrow;
+        std::vector<double> lval;
+        for (int bcol = 0; bcol < N; ++bcol) {
+            for (int arow = 0; arow < N; ++arow) {
+                const double l = d->bs_lower[(size_t)arow * N + bcol];
+                if (l > 0.0 && arow != gp && arow != gq && bcol != gp && bcol != gq) { lrow.push_back(arow); lval.push_back(l); }
+            }
+            lptr[bcol + 1] = (int32_t)lrow.size();
+        }
+        if (lrow.empty()) { lrow.push_back(0); lval.push_back(0.0); }   // upload() of an empty array leaves a null pointer
+        ok = ok && !upload(&p->low_ptr, lptr.data(), lptr.size());
+        ok = ok && !upload(&p->low_row, lrow.data(), lrow.size());
+        ok = ok && !upload(&p->low_val, lval.data(), lval.size());
     }
     ok = ok && !upload(&p->goal_edge_i, d->goal_edge_i, (size_t)d->n_goal_edges);
     ok = ok && !upload(&p->goal_edge_j, d->goal_edge_j, (size_t)d->n_goal_edges);
@@ -397,7 +420,7 @@ extern "C" int gik_plan_destroy(GikPlan *p)
     if (!p) return GIK_OK;
     void *ptrs[] = {p->slot_info, p->slot_target, p->deg, p->fast_info, p->fast_target, p->fast2_info, p->fast2_target, p->fast2_node, p->duo_info, p->duo_target, p->dense_target, p->dense_kind, p->dense_hub_kind, p->dense_hub_target, p->dense_goal_i, p->dense_goal_j,
                     p->dense_goal_slot, p->anchor_node, p->anchor_pos, p->bs_lower,
-                    p->bs_upper, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_ptr, p->omega_adj, p->omega_i,
+                    p->bs_upper, p->low_ptr, p->low_row, p->low_val, p->goal_edge_i, p->goal_edge_j, p->goal_edge_slot, p->omega_ptr, p->omega_adj, p->omega_i,
                     p->omega_j, p->T0, p->Trel, p->qs0, p->limit_i, p->limit_j, p->limit_lower, p->limit_upper};
     for (void *q : ptrs)
         if (q) cudaFree(q);
