@@ -849,7 +849,7 @@ extern "C" int gik_bounds_init(const GikPlan *p, const double *goal_d2, int32_t 
 }
 
 // Bytes of the per-call workspace of gik_bounds / gik_init / gik_bounds_init: 0 while the three N x N matrices of
-// a goal fit in shared memory (N <= 96), else the spilled matrices of every resident CTA.
+// a goal stay in shared memory, else the matrices every resident CTA keeps in L2 (see gik_plan.cu: bi_mode).
 extern "C" int64_t gik_workspace_bytes(const GikPlan *p)
 {
     if (!p || !p->bi_mode) return 0;

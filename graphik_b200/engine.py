@@ -97,7 +97,7 @@ class BatchIK:
 
     def _workspace(self):
         """Per-stream workspace of the bound-smoothing / initialisation kernel (None while everything fits in
-        shared memory, i.e. N <= 96)."""
+        shared memory: small graphs only, gik_workspace_bytes() says)."""
         if not self._ws_bytes:
             return None
         key = self.torch.cuda.current_stream(self.device).cuda_stream

@@ -165,9 +165,10 @@ int gik_hessvec(const GikPlan *plan, const double *Y, const double *W, const dou
  * out[B][N][3] = Z - Y * Omega,  Omega X + X Omega = Y^T Z - Z^T Y. */
 int gik_proj(int32_t N, const double *Y, const double *Z, int32_t B, double *out, void *stream);
 
-/* Per-call device workspace of gik_bounds / gik_init / gik_bounds_init in bytes: 0 for N <= 96 (everything
- * stays in shared memory; pass NULL), else the spilled N x N matrices of the resident CTAs.  The plan owns no
- * scratch memory: calls that may run concurrently (different streams) need one workspace each. */
+/* Per-call device workspace of gik_bounds / gik_init / gik_bounds_init in bytes: 0 when the three N x N matrices
+ * of a goal stay in shared memory (small graphs; pass NULL), else the N x N matrices the resident CTAs keep in L2
+ * (N > 20: the third matrix, which buys more CTAs per SM; N > 118: all three).  The plan owns no scratch memory:
+ * calls that may run concurrently (different streams) need one workspace each. */
 int64_t gik_workspace_bytes(const GikPlan *plan);
 
 /* bound_smoothing (dgp.py:192-231) for B goals: lb, ub [B][N][N] (unsquared). */
