@@ -33,6 +33,8 @@
 //
 // A pair carrying more than one term kind is not representable densely; gik_launch_rtr_cta then returns 1
 // and the caller falls back to k_rtr.
+#include <type_traits>
+
 #include "gik_rtr.cuh"
 
 namespace {
@@ -42,8 +44,9 @@ constexpr int kThreads = NPAD;              // thread t owns node t
 constexpr int kWarps = kThreads / 32;       // neighbour slices
 constexpr int kOwnWarps = kWarps;
 constexpr int kStride = 33;                 // row stride of a packed 32 x 32 block of c2
-constexpr int kRedA = 10, kRedB = 4;
-static_assert((NPAD + kWarps - 1) / kWarps <= 32, "one 32-bit activity mask per tile node");
+constexpr int kRedA = 18, kRedB = 18;
+constexpr int kMom = 32;                   // 15 moments of the tCG direction, 9 of the cached point (from 16)
+static_assert(NPAD / 2 <= 64, "one 64-bit activity mask per tile node: a neighbour slice never exceeds 64 nodes");
 
 // doubles of the packed symmetric pair cache: column block b holds b + 1 blocks of rows_b rows
 __host__ __device__ inline int c2_rows(int N, int b) { return min(32, N - 32 * b); }
@@ -66,11 +69,25 @@ struct CtaTables {
     int hub;                    // node whose pairs carry a second term (-1: none)
     const unsigned char *hub_kind;  // [N] kind of the second term of the pair (hub, i), 3 = none
     const double *hub_target;       // [N]
+    // all of the above are indexed by POSITION; perm[position] = node.  Positions >= jF form the equality clique,
+    // the 32-node blocks m >= mF lie inside it (mF = NB: no fast path)
+    const int32_t *perm;
+    int jF, mF;
 };
+
+// Contributions of one clique node at the doubled point X to the 9 constants of the point: m1 = sum X, M2 = sum X X^T
+// (xx, xy, xz, yy, yz, zz).  Explicit roundings: the same values must come out of every call site (a parked problem
+// recomputes what a running one carries).
+__device__ __forceinline__ void clique_consts(const double X[3], bool in, double *m)
+{
+    m[0] = in ? X[0] : 0.0; m[1] = in ? X[1] : 0.0; m[2] = in ? X[2] : 0.0;
+    m[3] = in ? __dmul_rn(X[0], X[0]) : 0.0; m[4] = in ? __dmul_rn(X[0], X[1]) : 0.0; m[5] = in ? __dmul_rn(X[0], X[2]) : 0.0;
+    m[6] = in ? __dmul_rn(X[1], X[1]) : 0.0; m[7] = in ? __dmul_rn(X[1], X[2]) : 0.0; m[8] = in ? __dmul_rn(X[2], X[2]) : 0.0;
+}
 
 // butterfly over a warp, lane 0 stores K partial sums
 template <int K>
-__device__ __forceinline__ void warp_sum_store(double (&v)[K], double *dst, bool store)
+__device__ __forceinline__ void warp_sum_store(double *v, double *dst, bool store)
 {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -85,7 +102,7 @@ __device__ __forceinline__ void warp_sum_store(double (&v)[K], double *dst, bool
 
 // every thread adds the owner warps' partial sums in the same order
 template <int K, int STRIDE>
-__device__ __forceinline__ void block_sum_load(double (&v)[K], const double *src)
+__device__ __forceinline__ void block_sum_load(double *v, const double *src)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -104,9 +121,32 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool first_of_own_warp = lane == 0;   // stores its warp's partial inner products
     const bool owner = tid < N;                     // thread tid owns node tid
-    const int JS = (N + kWarps - 1) / kWarps;
-    const int jlo = warp * JS;
-    const int jhi = max(jlo, min(N, jlo + JS));     // this warp's neighbour slice is [jlo, jhi)
+    // this warp's neighbour slice [jlo, jhi): equal COST per warp -- a neighbour outside the equality clique costs the full
+    // pair evaluation for every tile block, one inside it only for the blocks below mF (plus loads either way)
+    int jlo = 0, jhi = 0;
+    {
+        const int NBk = (N + 31) / 32;
+        const int mFk = tb.mF < NBk ? tb.mF : NBk;
+        const int c_full = 15 * NBk + 8, c_fast = 15 * mFk + 3 * (NBk - mFk) + 8;
+        const int total = c_full * min(tb.jF, N) + c_fast * max(0, N - tb.jF);
+        int acc = 0;
+        bool seen = false;
+        for (int j = 0; j < N; ++j) {
+            // neighbour j belongs to the warp whose share [w total / kWarps, (w + 1) total / kWarps) holds the middle of its cost
+            const int cj = j < tb.jF ? c_full : c_fast;
+            const int wj = min(kWarps - 1, (int)(((long long)(2 * acc + cj) * kWarps) / (2LL * total)));
+            acc += cj;
+            if (wj == warp) {
+                if (!seen) { jlo = j; seen = true; }
+                jhi = j + 1;
+            }
+        }
+        if (__syncthreads_or(jhi - jlo > 64)) {       // the 64-bit activity masks bound a slice: fall back to equal counts
+            const int JS = (N + kWarps - 1) / kWarps;
+            jlo = min(N, warp * JS);
+            jhi = min(N, jlo + JS);
+        }
+    }
     double *C2 = smem;                                  // packed symmetric 2 act (d - T) at the cached point
     double *P2 = C2 + c2_doubles(N);                    // [3][NPAD] 2 * coordinates of the cached point
     double *V = P2 + 3 * NPAD;                          // [3][NPAD] direction delta
@@ -117,10 +157,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
     double *Tp = redF + kWarps;                         // [NPAD] targets of the pairs (., p_n) for this problem
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
     double *Hc2 = Tq + NPAD;                            // [NPAD] 2 act (d - T) of the second terms around the hub node
-    double *goal = Hc2 + NPAD;                          // [n_goal]
+    double *RS = Hc2 + NPAD;                            // [kWarps][NPAD] slices' partial sums of c2 over the clique pairs
+    double *momS = RS + kWarps * NPAD;                  // [kMom] moments (block-uniform values kept out of the registers)
+    double *XW = momS + kMom;                           // [NPAD] <X_j, delta_j> of the clique nodes
+    double *goal = XW + NPAD;                           // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));                    // [0] work item, [1] park slot
     unsigned long long *s_t = reinterpret_cast<unsigned long long *>(s_b + 2);          // [0] problem start, [1] elapsed
     const int gp = tb.gp, gq = tb.gq;
+    const int jF = tb.jF, mF = tb.mF;
+    const bool has_fast = mF < NB;
+    const int node = owner ? tb.perm[tid] : 0;          // thread tid owns POSITION tid = node perm[tid]
+    const bool in_clique = owner && tid >= jF;
+    const bool fast_owner = owner && tid >= 32 * mF;     // its pairs with the clique go through the moments
+    const double m0 = (double)(N - jF);
     const GikSolveOpts &o = a.o;
     const double eps = 2.220446049250313e-16;
 
@@ -130,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
     __syncthreads();
 
     double xt[NB][3];           // 2 * coordinates of this lane's tile nodes at the cached point
-    uint32_t amask[NB];         // bit jj: term (tile node m, neighbour jlo + jj) active there
+    unsigned long long amask[NB];   // bit jj: term (tile node m, neighbour jlo + jj) active there
     uint32_t hact = 0u;         // bit m: second term of the pair (tile node m, hub) active there (hub's slice only)
     const int hub = tb.hub;
     const bool hub_warp = hub >= jlo && hub < jhi;   // this warp's slice contains the hub neighbour
@@ -140,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
         col_off[m] = 16 * m * (m + 1) * kStride + min(lane, c2_rows(N, m) - 1) * kStride;
-        amask[m] = 0u;
+        amask[m] = 0ull;
     }
     // offsets / strides of the NB reads for the neighbours j0, j0 + 1, ... inside block jb
     auto c2_walk = [&](int jb, int j0, int (&off)[NB], int (&step)[NB]) {
@@ -184,21 +233,52 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         if (owner) { buf[tid] = scale * v[0]; buf[NPAD + tid] = scale * v[1]; buf[2 * NPAD + tid] = scale * v[2]; }
     };
 
+    // direction delta -> V and, for clique nodes, <X_j, delta_j> -> XW (X = the doubled cached point; x in registers)
+    auto publish_dir = [&](const double (&v)[3], const double (&xown)[3]) {
+        if (owner) {
+            V[tid] = v[0]; V[NPAD + tid] = v[1]; V[2 * NPAD + tid] = v[2];
+            if (has_fast) XW[tid] = 2.0 * (xown[0] * v[0] + xown[1] * v[1] + xown[2] * v[2]);
+        }
+    };
+    // The 15 moments of the published direction over the clique (positions [jF, N)): e1 = sum delta, E = sum X delta^T,
+    // v3 = sum X <X, delta>.  Thread 8 k + p sums every 8th node for moment k, three butterfly steps finish it.  Runs
+    // between barriers (1) and (2), next to the pair pass; nothing rides on the latency chain of the iteration.
+    auto direction_moments = [&]() {
+        {
+            const int k = tid < 120 ? tid >> 3 : 14, part = tid & 7;   // the last eight threads repeat moment 14 and drop it
+            const double *A = k < 3 ? nullptr : P2 + (k < 12 ? (k - 3) / 3 : k - 12) * NPAD;
+            const double *Bv = k < 3 ? V + k * NPAD : (k < 12 ? V + ((k - 3) % 3) * NPAD : XW);
+            double s0 = 0.0, s1 = 0.0;
+            int jn = jF + part;
+            for (; jn + 8 < N; jn += 16) {
+                s0 = fma(A ? A[jn] : 1.0, Bv[jn], s0);
+                s1 = fma(A ? A[jn + 8] : 1.0, Bv[jn + 8], s1);
+            }
+            if (jn < N) s0 = fma(A ? A[jn] : 1.0, Bv[jn], s0);
+            double sm = s0 + s1;
+            sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 1);
+            sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 2);
+            sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 4);
+            if (part == 0 && tid < 120) momS[k] = sm;
+        }
+    };
+
     // costs.py:125-169 at the point published (doubled) in P2: rebuilds xt, C2 and the activity mask, leaves the
     // slices' partial half-gradients in Zp and their cost shares in redF.  Caller synchronises before and after.
     auto pair_pass_cost = [&]() {
         load_tile(P2, xt);
-        double gpart[NB][3];
+        double gpart[NB][3], rsum[NB];
         double fpart = 0.0;
 #pragma unroll
-        for (int m = 0; m < NB; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; amask[m] = 0u; }
+        for (int m = 0; m < NB; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; amask[m] = 0ull; rsum[m] = 0.0; }
         for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
             const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
             int off[NB], step[NB];
             c2_walk(jb, j0, off, step);
             for (int j = j0; j < j1; ++j) {
                 const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
-                const uint32_t bit = 1u << (j - jlo);
+                const unsigned long long bit = 1ull << (j - jlo);
+                const bool fj = j >= jF;
 #pragma unroll
                 for (int m = 0; m < NB; ++m) {
                     const int i = lane + 32 * m;
@@ -218,7 +298,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                     gpart[m][2] = fma(rr, dz, gpart[m][2]);
                     if (m <= jb) C2[off[m]] = 2.0 * rr;          // the mirrored pair computes the same bits
                     off[m] += step[m];
-                    amask[m] |= act ? bit : 0u;
+                    if (fj && m >= mF) rsum[m] += 2.0 * rr;      // clique pair: its c2 w term is split (pair_pass_hess)
+                    amask[m] |= act ? bit : 0ull;
                 }
             }
         }
@@ -258,6 +339,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
             }
         }
         store_partials(gpart);
+        if (has_fast) {
+#pragma unroll
+            for (int m = 0; m < NB; ++m) RS[warp * NPAD + lane + 32 * m] = rsum[m];
+        }
         if (hub_warp) {
             __syncwarp();
             if (lane == 0) {
@@ -275,28 +360,52 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         load_tile(V, wt);
 #pragma unroll
         for (int m = 0; m < NB; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
-        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
-            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
-            int off[NB], step[NB];
-            c2_walk(jb, j0, off, step);
-            uint32_t bit = 1u << (j0 - jlo);
+        // neighbours [ja, jb2) of one 32-node block; MF = first tile block whose pairs with these neighbours lie inside
+        // the equality clique (compile-time, so that the unrolled tile loop has no branches): for those only
+        // -c2_ij delta_j is accumulated here -- (sum_j c2_ij) delta_i and the <D,w> D part (15 moments of delta over the
+        // clique) are added by the node's owner
+        auto hess_range = [&](auto mf_tag, int ja, int jb2, int (&off)[NB], const int (&step)[NB], unsigned long long &bit) {
+            constexpr int MF = decltype(mf_tag)::value;
 #pragma unroll 2
-            for (int j = j0; j < j1; ++j) {
-                const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+            for (int j = ja; j < jb2; ++j) {
                 const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
+                double px = 0.0, py = 0.0, pz = 0.0;
+                if (MF > 0) { px = P2[j]; py = P2[NPAD + j]; pz = P2[2 * NPAD + j]; }
 #pragma unroll
                 for (int m = 0; m < NB; ++m) {
                     const double c2 = C2[off[m]];
                     off[m] += step[m];
-                    const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
-                    const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
-                    double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
-                    s = (amask[m] & bit) ? s : 0.0;
-                    z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
-                    z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
-                    z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                    if (m >= MF) {
+                        z[m][0] = fma(-c2, vx, z[m][0]);
+                        z[m][1] = fma(-c2, vy, z[m][1]);
+                        z[m][2] = fma(-c2, vz, z[m][2]);
+                    } else {
+                        const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                        const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
+                        double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
+                        s = (amask[m] & bit) ? s : 0.0;
+                        z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
+                        z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
+                        z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                    }
                 }
                 bit <<= 1;
+            }
+        };
+        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
+            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
+            int off[NB], step[NB];
+            c2_walk(jb, j0, off, step);
+            unsigned long long bit = 1ull << (j0 - jlo);
+            const int jm = has_fast ? min(max(j0, jF), j1) : j1;     // [j0, jm): no clique neighbour, [jm, j1): clique
+            hess_range(std::integral_constant<int, NB>(), j0, jm, off, step, bit);
+            if (jm < j1) {
+                switch (mF) {
+                    case 0: hess_range(std::integral_constant<int, 0>(), jm, j1, off, step, bit); break;
+                    case 1: hess_range(std::integral_constant<int, (1 < NB ? 1 : NB)>(), jm, j1, off, step, bit); break;
+                    case 2: hess_range(std::integral_constant<int, (2 < NB ? 2 : NB)>(), jm, j1, off, step, bit); break;
+                    default: hess_range(std::integral_constant<int, (3 < NB ? 3 : NB)>(), jm, j1, off, step, bit); break;
+                }
             }
         }
         double react[3] = {0.0, 0.0, 0.0};
@@ -337,6 +446,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         return f;
     };
 
+    auto gather_rs = [&]() -> double {
+        double acc = RS[tid];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) acc += RS[w * NPAD + tid];
+        return acc;
+    };
+    // owner of a node whose clique pairs took the fast path: Z_i += sum_j (X_i - X_j)(X_i - X_j)^T (w_i - w_j) over the clique
+    // (moments in momS) + (sum_j c2_ij) w_i
+    auto add_clique_terms = [&](double (&Z)[3], const double (&xo)[3], const double (&w)[3], double rs) {
+        const double X[3] = {2.0 * xo[0], 2.0 * xo[1], 2.0 * xo[2]};
+        const double *e1 = momS, *E = momS + 3, *v3 = momS + 12, *m1 = momS + 16, *M2 = momS + 19;
+        const double xd = X[0] * w[0] + X[1] * w[1] + X[2] * w[2];
+        const double beta = E[0] + E[4] + E[8];
+        const double sc = fma(m0, xd, beta) - (X[0] * e1[0] + X[1] * e1[1] + X[2] * e1[2]) -
+                          (m1[0] * w[0] + m1[1] * w[1] + m1[2] * w[2]);
+        const double Mw[3] = {M2[0] * w[0] + M2[1] * w[1] + M2[2] * w[2], M2[1] * w[0] + M2[3] * w[1] + M2[4] * w[2],
+                              M2[2] * w[0] + M2[4] * w[1] + M2[5] * w[2]};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double EX = E[3 * q] * X[0] + E[3 * q + 1] * X[1] + E[3 * q + 2] * X[2];
+            Z[q] += fma(X[q], sc, fma(-m1[q], xd, EX + Mw[q] - v3[q])) + rs * w[q];
+        }
+    };
+
     // parked problems of the incoming queue are resumed before any new problem starts (gik_rtr.cuh)
     int n_res = 0;
     if (a.carry_in) {
@@ -359,10 +492,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
 
         double x[3] = {0.0, 0.0, 0.0}, g[3] = {0.0, 0.0, 0.0}, eta[3], Heta[3], r[3], dl[3], Hd[3] = {0.0, 0.0, 0.0};
         if (owner) {
-            const double *src = resumed ? ent + CW_X + 3 * tid : a.Y_init + ((size_t)b * N + tid) * 3;
+            const double *src = resumed ? ent + CW_X + 3 * node : a.Y_init + ((size_t)b * N + node) * 3;
             x[0] = src[0]; x[1] = src[1]; x[2] = src[2];
             if (resumed) {
-                src = ent + CW_X + 3 * (N + tid);
+                src = ent + CW_X + 3 * (N + node);
                 g[0] = src[0]; g[1] = src[1]; g[2] = src[2];
             }
         }
@@ -385,8 +518,26 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         }
         __syncthreads();
 
-        double fx, gg, Mi[6], Delta;
+        double fx, gg, Mi[6], Delta, rs = 0.0;
         int k_outer, inner_total;
+        // clique constants of the cached point (momS[16..25)) and this node's sum of c2 over its clique pairs; needs the
+        // pair pass at x behind a barrier.  The same per-thread values and the same summation tree as at an accepted step.
+        auto refresh_clique = [&]() {
+            if (!has_fast) return;
+            if (owner) rs = gather_rs();
+            const double X[3] = {2.0 * x[0], 2.0 * x[1], 2.0 * x[2]};
+            double cc[9];
+            clique_consts(X, in_clique, cc);
+            warp_sum_store<9>(cc, redB + warp * kRedB, first_of_own_warp);
+            __syncthreads();
+            if (tid < 9) {          // the sum block_sum_load forms, without indexing a register array by tid
+                double sm = redB[tid];
+#pragma unroll
+                for (int w = 1; w < kOwnWarps; ++w) sm += redB[w * kRedB + tid];
+                momS[16 + tid] = sm;
+            }
+            __syncthreads();
+        };
         if (resumed) {
             fx = ent[CW_FX]; gg = ent[CW_GG]; Delta = ent[CW_DELTA];
 #pragma unroll
@@ -396,6 +547,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
             inner_total = (int)(cnt >> 32);
             if (tid == 0) s_t[0] = entp[CW_T0];
             pair_pass_cost();   // tile, pair cache and activity masks at x, as after a rejected step
+            __syncthreads();
+            refresh_clique();
         } else {
             pair_pass_cost();
             __syncthreads();
@@ -413,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
             k_outer = 0;
             inner_total = 0;
             if (tid == 0) s_t[0] = a.maxtime_ns ? gik_globaltimer() : 0ull;
+            refresh_clique();
         }
         const int inner_entry = inner_total;
         bool may_park = a.carry_out != nullptr;
@@ -436,13 +590,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                 int stop = MAX_INNER_ITER;
                 int j = 0;
                 __syncthreads();          // every reader of V / redA / redB of the previous phase is done
-                publish(V, dl, 1.0);
+                publish_dir(dl, x);
                 for (j = 0; j < o.maxinner; ++j) {
                     __syncthreads();                                   // (1) delta published
+                    if (has_fast) direction_moments();                 // -> momS, read by the owners after barrier (2)
                     pair_pass_hess();
                     __syncthreads();                                   // (2) partial sums complete
                     if (owner) gather(Hd);                             // raw Z; projected below
                     else { Hd[0] = 0.0; Hd[1] = 0.0; Hd[2] = 0.0; }
+                    if (fast_owner) add_clique_terms(Hd, x, dl, rs);
                     double v[7];
                     v[0] = dl[0] * Hd[0] + dl[1] * Hd[1] + dl[2] * Hd[2];
                     v[1] = Hd[1] * x[2] - Hd[2] * x[1];                // c = sum Z_i x Y_i
@@ -513,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                     for (int q = 0; q < 3; ++q) dl[q] = fma(beta, dl[q], -r[q]);
                     e_Pd = beta * (e_Pd + alpha * d_Pd);
                     d_Pd = z_r + beta * beta * d_Pd;
-                    publish(V, dl, 1.0);        // the pair pass read V before barrier (2)
+                    publish_dir(dl, x);            // the pair pass read V before barrier (2)
                 }
                 const int numit = j < o.maxinner ? j : o.maxinner - 1;
 
@@ -527,15 +683,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                 __syncthreads();
                 if (owner) gather(Hd);
                 else { Hd[0] = 0.0; Hd[1] = 0.0; Hd[2] = 0.0; }
-                double v[9];
+                const double rs_prop = (has_fast && owner) ? gather_rs() : 0.0;
+                double v[18];
                 v[0] = g[0] * eta[0] + g[1] * eta[1] + g[2] * eta[2];
                 v[1] = eta[0] * Heta[0] + eta[1] * Heta[1] + eta[2] * Heta[2];
                 v[2] = Hd[0] * Hd[0] + Hd[1] * Hd[1] + Hd[2] * Hd[2];
                 v[3] = dl[0] * dl[0]; v[4] = dl[0] * dl[1]; v[5] = dl[0] * dl[2];
                 v[6] = dl[1] * dl[1]; v[7] = dl[1] * dl[2]; v[8] = dl[2] * dl[2];
-                warp_sum_store<9>(v, redA + warp * kRedA, first_of_own_warp);
-                __syncthreads();
-                block_sum_load<9, kRedA>(v, redA);
+                if (has_fast) {
+                    const double X[3] = {2.0 * dl[0], 2.0 * dl[1], 2.0 * dl[2]};
+                    clique_consts(X, in_clique, v + 9);
+                    warp_sum_store<18>(v, redA + warp * kRedA, first_of_own_warp);
+                    __syncthreads();
+                    block_sum_load<18, kRedA>(v, redA);
+                } else {
+                    warp_sum_store<9>(v, redA + warp * kRedA, first_of_own_warp);
+                    __syncthreads();
+                    block_sum_load<9, kRedA>(v, redA);
+                }
                 const double fx_prop = total_cost();
                 double rhonum = fx - fx_prop;
                 double rhoden = -v[0] - 0.5 * v[1];
@@ -558,6 +723,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
                     gg = v[2];
                     norm_grad = sqrt(gg);
                     gik_sylvester_inverse(v + 3, Mi);
+                    rs = rs_prop;
+                    if (has_fast && tid < 9) {   // read after the barriers of the next tCG start
+                        double sm = redA[9 + tid];
+#pragma unroll
+                        for (int w = 1; w < kOwnWarps; ++w) sm += redA[w * kRedA + 9 + tid];
+                        momS[16 + tid] = sm;
+                    }
                 } else {
                     // rejected: bring the exchange buffer, the tile and the pair cache back to x
                     __syncthreads();
@@ -598,10 +770,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
         double *Yrow = resumed ? reinterpret_cast<double *>(entp[CW_Y]) : a.Y_out + (size_t)b * N * 3;
         double *cx = status == GIK_STATUS_PENDING ? gik_carry_slot(a.carry_out, park_slot) : nullptr;
         if (owner) {
-            double *dst = Yrow + tid * 3;
+            double *dst = Yrow + node * 3;
             dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
             if (cx) {
-                dst = cx + CW_X + 3 * tid;
+                dst = cx + CW_X + 3 * node;
                 dst[0] = x[0]; dst[1] = x[1]; dst[2] = x[2];
                 dst += 3 * N;
                 dst[0] = g[0]; dst[1] = g[1]; dst[2] = g[2];
@@ -619,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const 
 size_t cta_smem_bytes(int N, int n_goal)
 {
     const int goal_pad = (n_goal + 1) & ~1;
-    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 3) * NPAD + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
+    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 3 + kWarps + 1) * NPAD + kMom + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
                       sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned long long);
     return (smem + 15) & ~(size_t)15;
 }
@@ -660,8 +832,12 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     tb.goal_j = p->dense_goal_j;
     tb.goal_slot = p->dense_goal_slot;
     tb.n_goal_edges = p->n_dense_goal;
-    tb.gp = p->n_dense_goal > 0 ? p->goal_p : -1;
-    tb.gq = p->n_dense_goal > 0 ? p->goal_q : -1;
+    tb.gp = p->n_dense_goal > 0 ? p->dense_goal_p : -1;
+    tb.gq = p->n_dense_goal > 0 ? p->dense_goal_q : -1;
+    tb.perm = p->dense_perm;
+    tb.jF = p->dense_clique_start;
+    tb.mF = (p->dense_clique_start + 31) / 32;      // first 32-node block that lies inside the clique
+    if (tb.mF > (N + 31) / 32) tb.mF = (N + 31) / 32;
     tb.hub = p->dense_hub;
     tb.hub_kind = p->dense_hub_kind;
     tb.hub_target = p->dense_hub_target;

@@ -247,7 +247,8 @@ def test_end_state_vs_reference_sample(name):
           "median iters gpu %d ref %d" % (same.sum(), len(same), np.mean(pos < 1e-2), np.mean(ref_ok),
                                           np.median(f), np.median(g["f"]),
                                           np.median(out["iterations"].cpu().numpy()), np.median(g["iterations"])))
-    assert np.mean(same) >= 0.6
+    # observed with the round-2 kernels: UR10 51/64, KUKA 62/64, LWA4D 47/48, LWA4P 45/48, Panda 48/48
+    assert np.mean(same) >= {"ur10": 0.75, "kuka": 0.9, "lwa4d": 0.9, "lwa4p": 0.85, "panda": 0.95}[name]
     # a goal may end in a local minimum in one run and not in the other (rounding-perturbed trajectories):
     # compare rates, not goal by goal
     assert np.mean(f[ref_conv] < 1e-9) >= 0.9
@@ -260,6 +261,38 @@ def test_end_state_vs_reference_sample(name):
         Dg = np.linalg.norm(out["x"][k].cpu().numpy()[:, None] - out["x"][k].cpu().numpy()[None], axis=-1)
         Dr = np.linalg.norm(g["Y_sol"][k][:, None] - g["Y_sol"][k][None], axis=-1)
         assert np.max(np.abs(Dg - Dr)) < (1e-3 if robot.n == 6 else 5e-2)
+
+
+@pytest.mark.parametrize("name", ["ur10", "kuka", "lwa4d", "lwa4p", "panda", "chain20"])
+def test_product_pipeline_with_its_own_initialisation_vs_reference_sample(name):
+    """The same reference samples, but through the PRODUCT pipeline end to end (BatchIK.solve: goal distances, bound
+    smoothing, the kernel's own initialisation, solve, joint recovery) -- nothing of the reference is injected.  The
+    kernel's Y_init equals the reference's only up to LAPACK's eigenvector signs, i.e. it is another valid
+    draw of the same initialisation rule, so what must agree are the RATES: converged fraction, pose success, and the
+    iteration statistics."""
+    import os
+    from helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, name + "_stats.npz")):
+        pytest.skip("reference sample not generated")
+    robot, graph, eng = _engine(name)
+    g = golden(name + "_stats")
+    T = g["T_goal"]
+    out = eng.solve(T, check=True)
+    f, it = out["f(x)"].cpu().numpy(), out["iterations"].cpu().numpy()
+    pos = out["pos_err"].cpu().numpy()
+    n = len(f)
+    print(name, "own init: converged gpu %.3f ref %.3f; pose success gpu %.3f ref %.3f; median iters gpu %d ref %d"
+          % (np.mean(f < 1e-9), np.mean(g["f"] < 1e-9), np.mean(pos < 1e-2), np.mean(g["pose_err"] < 1e-2),
+             np.median(it), np.median(g["iterations"])))
+    tol = 0.02 + 0.8 / np.sqrt(n)     # two binomial samples of n goals (2 sigma of their difference ~ 0.11 at n = 64)
+    assert abs(np.mean(f < 1e-9) - np.mean(g["f"] < 1e-9)) <= tol
+    assert abs(np.mean(pos < 1e-2) - np.mean(g["pose_err"] < 1e-2)) <= tol
+    r = np.median(it) / np.median(g["iterations"])
+    assert 0.6 < r < 1.6, r
+    # the joint angles returned reproduce the goal wherever the solve converged to a realisation
+    T_sol, _ = eng.fk(out["q"], want_points=False)
+    err = np.linalg.norm(T_sol.cpu().numpy()[:, :3, 3] - T[:, :3, 3], axis=1)
+    assert np.allclose(err, pos, atol=1e-9)
 
 
 @pytest.mark.parametrize("name", ["chain20", "kuka_table", "kuka_table_intended"])

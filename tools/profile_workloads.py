@@ -19,6 +19,11 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    for a in sys.argv[1:]:
+        if a.startswith("--lib="):       # an A/B variant built by hand into graphik_b200/lib/
+            from graphik_b200 import _lib
+            _lib.LIBPATH = os.path.join(_lib.LIBDIR, a[6:])
+            _lib.needs_build = lambda: False
     import torch
     from bench import goals_for, load_workload, measured_peak_hbm
     from graphik_b200.engine import BatchIK
@@ -28,6 +33,8 @@ def main():
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak, _ = measured_peak_hbm()
     for spec in sys.argv[1:]:
+        if spec.startswith("--"):
+            continue
         parts = spec.split(":")
         robot_name, B = parts[0], int(parts[1])
         kernel = parts[2] if len(parts) > 2 and parts[2] else "auto"
