@@ -234,8 +234,9 @@ class IKStream:
             self._finalise(tk)
 
     def reserve(self, n_batches, B):
-        """Prime torch's caching allocator for `n_batches` outstanding batches of B goals: without it the first pass
-        over a long stream calls cudaMalloc from submit(), and cudaMalloc waits for the running launch."""
+        """Prime torch's caching allocator for `n_batches` outstanding batches of B goals (and, for a to_host stream, pin
+        its ring of result buffers): without it the first pass over a long stream calls cudaMalloc / cudaHostAlloc from
+        submit() and result(), and those wait for the running launch."""
         eng, torch = self.eng, self.torch
         N, n, ng = eng.plan.N, max(eng.plan.n_joints, 1), max(eng.plan.n_goal, 1)
         per_slot = -(-int(n_batches) // len(self.slots))
@@ -249,6 +250,12 @@ class IKStream:
                                  eng._empty(B, dtype=torch.int32), eng._empty(B, dtype=torch.int32), eng._empty(B, n),
                                  eng._empty(B, n)]
                     del hold
+                if self.to_host:       # ... and the ring of pinned result buffers (pinning memory costs milliseconds)
+                    ring = sl.host_ring.setdefault(int(B), [])
+                    while len(ring) < self.HOST_RING:
+                        ring.append({"q": torch.empty((B, eng.plan.n_joints), dtype=torch.float64).pin_memory(),
+                                     "f(x)": torch.empty((B,), dtype=torch.float64).pin_memory(),
+                                     "status": torch.empty((B,), dtype=torch.int32).pin_memory()})
                 sl.stream.synchronize()
 
     def drain_slot(self, sl):
