@@ -108,138 +108,6 @@ k_costs(PlanView pv, const double *__restrict__ Y, const double *__restrict__ Wd
     }
 }
 
-// ---------------------------------------------------------------- TMA-fed streaming form
-// The kernels above hold ONE problem per group in flight: load, publish, compute, store.  At ~1 us of HBM latency a B200
-// needs ~40 KB of reads in flight per SM to run at its bandwidth; 32 resident warps with 384 B each give 12 KB, and
-// the kernels sat at 0.25-0.40 of the measured HBM peak.  Here every group owns a ring of S stages in shared memory
-// that its leader lane fills with 1-D bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): the
-// problem S - 1 ahead is already on its way while the group computes.  The copies land as they lie in HBM (Y[b] is
-// [N][3]), so neighbour coordinates are read from the stage directly and the publish step is gone.
-__device__ __forceinline__ uint32_t gik_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void gik_mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gik_smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void gik_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gik_smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void gik_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(gik_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gik_smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void gik_mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "GIK_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra GIK_DONE;\n"
-        "bra GIK_WAIT;\n"
-        "GIK_DONE:\n"
-        "}\n" ::"r"(gik_smem_u32(bar)), "r"(parity) : "memory");
-}
-
-template <int W, int NPL, int MODE, int S>
-__global__ void __launch_bounds__(kThreads)
-k_costs_pipe(PlanView pv, const double *__restrict__ Y, const double *__restrict__ Wd,
-             const double *__restrict__ goal_d2, int B, double *__restrict__ f, double *__restrict__ out)
-{
-    constexpr int GPB = kThreads / W;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int gid = threadIdx.x / W, lane = threadIdx.x % W;
-    const int N = pv.N;
-    const uint32_t ybytes = (uint32_t)N * 24u, gbytes = (uint32_t)pv.n_goal * 8u;      // multiples of 16 (host check)
-    const uint32_t stage_bytes = ybytes * (MODE == 1 ? 2u : 1u) + gbytes;
-    unsigned char *ring = smem_raw + (size_t)gid * (S * stage_bytes + 16 * ((S * 8 + 15) / 16));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + S * stage_bytes);
-    const unsigned mask = gik_group_mask<W>();
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) gik_mbar_init(bars + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp(mask);
-    const int first = blockIdx.x * GPB + gid, step = gridDim.x * GPB;
-    const size_t stride = (size_t)3 * N;
-    auto issue = [&](int k) {
-        const long long b = (long long)first + (long long)k * step;
-        if (lane == 0 && b < B) {
-            unsigned char *dst = ring + (size_t)(k % S) * stage_bytes;
-            uint64_t *bar = bars + (k % S);
-            gik_mbar_expect_tx(bar, stage_bytes);
-            gik_bulk_g2s(dst, Y + (size_t)b * stride, ybytes, bar);
-            if (MODE == 1) gik_bulk_g2s(dst + ybytes, Wd + (size_t)b * stride, ybytes, bar);
-            if (gbytes) gik_bulk_g2s(dst + ybytes * (MODE == 1 ? 2u : 1u), goal_d2 + (size_t)b * pv.n_goal, gbytes, bar);
-        }
-    };
-#pragma unroll
-    for (int k = 0; k < S; ++k) issue(k);
-    for (int k = 0;; ++k) {
-        const long long b = (long long)first + (long long)k * step;
-        if (b >= B) break;
-        gik_mbar_wait(bars + (k % S), (uint32_t)(k / S) & 1u);
-        const double *P = reinterpret_cast<const double *>(ring + (size_t)(k % S) * stage_bytes);   // [N][3]
-        const double *V = P + stride;                                                                // [N][3] (MODE 1)
-        const double *goal = P + stride * (MODE == 1 ? 2 : 1);
-        double fpart = 0.0;
-#pragma unroll
-        for (int m = 0; m < NPL; ++m) {
-            const int i = lane + W * m;
-            if (i >= N) continue;
-            const double x0 = P[3 * i], x1 = P[3 * i + 1], x2 = P[3 * i + 2];
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-            if (MODE == 1) { w0 = V[3 * i]; w1 = V[3 * i + 1]; w2 = V[3 * i + 2]; }
-            const int dg = pv.deg[i];
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            for (int kk = 0; kk < dg; ++kk) {
-                const uint32_t info = pv.slot_info[kk * N + i];
-                const int j = GIK_SLOT_NBR(info);
-                const uint32_t kind = GIK_SLOT_KIND(info);
-                const uint32_t gs = GIK_SLOT_GOAL(info);
-                const double T = gs ? goal[gs - 1] : pv.slot_target[kk * N + i];
-                const double dx = x0 - P[3 * j], dy = x1 - P[3 * j + 1], dz = x2 - P[3 * j + 2];
-                const double d = gik_sqdist(dx, dy, dz);
-                double r = d - T;
-                const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (r < 0.0)) |
-                                 ((kind == GIK_TERM_UP) & (r > 0.0));
-                if (MODE == 0) {                       // costs.py:125-169, as gik_pass_cost_grad
-                    r = act ? r : 0.0;
-                    fpart = fma(r, r, fpart);
-                    a0 = fma(r, dx, a0);
-                    a1 = fma(r, dy, a1);
-                    a2 = fma(r, dz, a2);
-                } else {                               // costs.py:171-207, as gik_pass_hess
-                    const double wx = w0 - V[3 * j], wy = w1 - V[3 * j + 1], wz = w2 - V[3 * j + 2];
-                    const double s = dx * wx + dy * wy + dz * wz;
-                    const double a = act ? 2.0 * s : 0.0;
-                    const double bq = act ? r : 0.0;
-                    a0 = fma(a, dx, fma(bq, wx, a0));
-                    a1 = fma(a, dy, fma(bq, wy, a1));
-                    a2 = fma(a, dz, fma(bq, wz, a2));
-                }
-            }
-            if (out) {
-                double *dst = out + (size_t)b * stride + 3 * i;
-                dst[0] = 2.0 * a0; dst[1] = 2.0 * a1; dst[2] = 2.0 * a2;
-            }
-        }
-        if (MODE == 0) {
-            double v[1] = {0.5 * fpart};
-            gik_allreduce<W, 1>(v, mask);
-            if (f && lane == 0) f[b] = v[0];
-        }
-        __syncwarp(mask);          // the group has finished reading the stage
-        issue(k + S);
-    }
-}
-
 // Same operators for N <= 32 with the lane-centric tables of the solver's latency kernel: one warp per
 // problem, LPN lanes per node, the slot description of a lane lives in registers for the whole launch,
 // so a problem costs one coalesced read of Y (and W), the edge pass, and one coalesced write.
@@ -432,48 +300,10 @@ int launch_costs_fast(const GikPlan *p, const double *Y, const double *Wd, const
     return gik_check_cuda(cudaGetLastError(), "k_costs_fast launch");
 }
 
-template <int W, int NPL, int MODE>
-int launch_costs_pipe(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
-                      double *f, double *out, cudaStream_t st)
-{
-    constexpr int GPB = kThreads / W, S = 3;
-    const size_t stage = (size_t)p->N * 24 * (MODE == 1 ? 2 : 1) + (size_t)p->n_goal * 8;
-    const size_t smem = (size_t)GPB * (S * stage + 16 * ((S * 8 + 15) / 16));
-    auto kern = k_costs_pipe<W, NPL, MODE, S>;
-    static int attr_dev = -1;
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && (attr_dev != p->device || attr_smem < smem)) {
-        GIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_dev = p->device;
-        attr_smem = smem;
-    }
-    int blocks = (B + GPB - 1) / GPB;
-    const int cap = p->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    kern<<<blocks, kThreads, smem, st>>>(view_of(p), Y, Wd, goal_d2, B, f, out);
-    return gik_check_cuda(cudaGetLastError(), "k_costs_pipe launch");
-}
-
-// bulk copies need 16-byte aligned sources and sizes: rows of N x 3 doubles with N even, goal rows with n_goal even
-bool pipe_ok(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2)
-{
-    const uintptr_t a = (uintptr_t)Y | (uintptr_t)Wd | (uintptr_t)goal_d2;
-    const size_t stage = (size_t)p->N * 48 + (size_t)p->n_goal * 8;
-    return (p->N % 2 == 0) && (p->n_goal % 2 == 0) && (a % 16 == 0) && stage * 3 * (kThreads / p->W) <= 200 * 1024;
-}
-
 template <int MODE>
 int dispatch_costs(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
                    double *f, double *out, cudaStream_t st)
 {
-    if (pipe_ok(p, Y, Wd, goal_d2)) {
-        if (p->W == 16) return launch_costs_pipe<16, 1, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
-        switch (p->NPL) {
-            case 1: return launch_costs_pipe<32, 1, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
-            case 2: return launch_costs_pipe<32, 2, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
-            default: return launch_costs_pipe<32, 4, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
-        }
-    }
     // 17..32 nodes: warp per problem with register-resident slot tables (KUKA: 1.4x the group kernel);
     // N <= 16 stays on the 16-lane groups, which put two problems in a warp (measured faster there)
     if (p->fast_info && p->fast_LPN == 1) {
