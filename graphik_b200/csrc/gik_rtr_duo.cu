@@ -64,13 +64,16 @@ __host__ __device__ constexpr int duo_smem_doubles(int SPL, int goal_pad)
 // shared memory and 8 warps / SM (248 registers) run at the same 2.11 G tCG iterations / s -- the shared-memory pipe is
 // the common limit (168 wavefronts per trip, 43 % of them cache reads) -- so up to 9 slots the cache moves into the
 // registers that 8 warps / SM leave free.
+#ifndef GIK_DUO_MINB
+#define GIK_DUO_MINB 8     // resident warps per SM with the slot cache in registers (A/B: tools/, -DGIK_DUO_MINB=...)
+#endif
 #ifndef GIK_DUO_REGCACHE
 #define GIK_DUO_REGCACHE 1
 #endif
 __host__ __device__ constexpr bool duo_cache_in_regs(int SPL) { return GIK_DUO_REGCACHE && SPL <= 9; }
 
 template <int SPL>
-__global__ void __launch_bounds__(kThreads, duo_cache_in_regs(SPL) ? 8 : 12) k_rtr_duo(const RtrArgs a, const uint32_t *__restrict__ duo_info,
+__global__ void __launch_bounds__(kThreads, duo_cache_in_regs(SPL) ? GIK_DUO_MINB : 12) k_rtr_duo(const RtrArgs a, const uint32_t *__restrict__ duo_info,
                                                           const double *__restrict__ duo_target)
 {
     constexpr bool RC = duo_cache_in_regs(SPL);

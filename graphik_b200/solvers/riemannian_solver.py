@@ -48,7 +48,10 @@ class RiemannianSolver:
         (riemannian_solver.py:222); to keep that usage cheap the engine is cached on the graph object and
         rebuilt only when the graph's edge data changed (e.g. an obstacle was added)."""
         g = self.graph
-        sig = hash((g.number_of_nodes(), g.dist.tobytes(), g.lower.tobytes(), g.upper.tobytes(),
+        import torch
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1   # a plan belongs to one device
+        sig = hash((dev, tuple(sorted((k, repr(v)) for k, v in self.params.items())),
+                    g.number_of_nodes(), g.dist.tobytes(), g.lower.tobytes(), g.upper.tobytes(),
                     g.below.tobytes(), g.above.tobytes()))
         cached = getattr(g, "_gik_engine_cache", None)
         if self._engine is None and cached is not None and cached[0] == sig:
