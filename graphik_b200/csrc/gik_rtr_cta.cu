@@ -40,10 +40,9 @@
 namespace {
 
 constexpr int NPAD = 128;
-constexpr int kOwnWarps = NPAD / 32;        // warps 0..3: thread t owns node t (solver state, reductions, latency chain)
-constexpr int kSlices = 4;                  // neighbour slices per role
-constexpr int kWarps = 2 * kSlices;         // + warps 4..7: pair passes only
-constexpr int kThreads = 32 * kWarps;
+constexpr int kThreads = NPAD;              // thread t owns node t
+constexpr int kWarps = kThreads / 32;       // neighbour slices
+constexpr int kOwnWarps = kWarps;
 constexpr int kStride = 33;                 // row stride of a packed 32 x 32 block of c2
 constexpr int kRedA = 18, kRedB = 18;
 constexpr int kMom = 32;                   // 15 moments of the tCG direction, 9 of the cached point (from 16)
@@ -114,74 +113,59 @@ __device__ __forceinline__ void block_sum_load(double *v, const double *src)
     }
 }
 
-// NB = 32-node blocks of the graph, MS = how many of them the OWNER warps take in the pair passes (the others go to the
-// worker warps).  With an equality clique MS = mF: the owner warps evaluate the blocks that need the full pair
-// evaluation against every neighbour, the workers the clique blocks (3 FP64 per pair against clique neighbours).
-//
-// The body is instantiated once per ROLE (0: owner warps, 1: worker warps) and the kernel branches on the warp index
-// once, at its top: in the workers' instantiation every thread is a non-owner, all solver state is the constant zero
-// and the compiler drops it -- what remains are the pair passes, the block-uniform scalar chain and the barriers, which
-// both instantiations execute in the same order.
-template <int NB, int MS, int ROLE>
-__device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
+template <int NB>   // 32-node blocks = nodes per lane in the pair passes
+__global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const CtaTables tb)
 {
-    constexpr int TC = ROLE ? NB - MS : MS;            // tile blocks per lane of this role
-    constexpr int NT = TC;
-    constexpr int role = ROLE;
-    constexpr int mbase = ROLE ? MS : 0;               // first block of this role's tile
     extern __shared__ double smem[];
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slice = warp % kSlices;
-    const bool first_of_own_warp = lane == 0 && ROLE == 0;   // stores its warp's partial inner products
-    const bool owner = ROLE == 0 && tid < N;       // thread tid owns node tid (N <= 128: owner warps only)
+    const bool first_of_own_warp = lane == 0;   // stores its warp's partial inner products
+    const bool owner = tid < N;                     // thread tid owns node tid
     // this warp's neighbour slice [jlo, jhi): equal COST per warp -- a neighbour outside the equality clique costs the full
     // pair evaluation for every tile block, one inside it only for the blocks below mF (plus loads either way)
     int jlo = 0, jhi = 0;
     {
-        // cost of a neighbour for this role: its blocks x (15 FP64 for the full pair evaluation | 3 for a clique pair)
-        const int mc = role ? NB - MS : MS;
-        const bool role_fast = role == 1 && tb.mF < NB;
-        const int c_full = 15 * mc + 8, c_fast = (role_fast ? 3 : 15) * mc + 8;
+        const int NBk = (N + 31) / 32;
+        const int mFk = tb.mF < NBk ? tb.mF : NBk;
+        const int c_full = 15 * NBk + 8, c_fast = 15 * mFk + 3 * (NBk - mFk) + 8;
         const int total = c_full * min(tb.jF, N) + c_fast * max(0, N - tb.jF);
         int acc = 0;
         bool seen = false;
         for (int j = 0; j < N; ++j) {
             // neighbour j belongs to the warp whose share [w total / kWarps, (w + 1) total / kWarps) holds the middle of its cost
             const int cj = j < tb.jF ? c_full : c_fast;
-            const int wj = min(kSlices - 1, (int)(((long long)(2 * acc + cj) * kSlices) / (2LL * total)));
+            const int wj = min(kWarps - 1, (int)(((long long)(2 * acc + cj) * kWarps) / (2LL * total)));
             acc += cj;
-            if (wj == slice) {
+            if (wj == warp) {
                 if (!seen) { jlo = j; seen = true; }
                 jhi = j + 1;
             }
         }
         if (__syncthreads_or(jhi - jlo > 64)) {       // the 64-bit activity masks bound a slice: fall back to equal counts
-            const int JS = (N + kSlices - 1) / kSlices;
-            jlo = min(N, slice * JS);
+            const int JS = (N + kWarps - 1) / kWarps;
+            jlo = min(N, warp * JS);
             jhi = min(N, jlo + JS);
         }
     }
     double *C2 = smem;                                  // packed symmetric 2 act (d - T) at the cached point
     double *P2 = C2 + c2_doubles(N);                    // [3][NPAD] 2 * coordinates of the cached point
     double *V = P2 + 3 * NPAD;                          // [3][NPAD] direction delta
-    double *Zp = V + 3 * NPAD;                          // [kSlices][3][NPAD] partial node sums of the slices
-    double *redA = Zp + kSlices * 3 * NPAD;             // [kOwnWarps][kRedA]
+    double *Zp = V + 3 * NPAD;                          // [kWarps][3][NPAD] partial node sums of the slices
+    double *redA = Zp + kWarps * 3 * NPAD;              // [kOwnWarps][kRedA]
     double *redB = redA + kOwnWarps * kRedA;            // [kOwnWarps][kRedB]
-    double *redF = redB + kOwnWarps * kRedB;            // [kWarps] cost shares of the warps
+    double *redF = redB + kOwnWarps * kRedB;            // [kWarps] cost shares of the slices
     double *Tp = redF + kWarps;                         // [NPAD] targets of the pairs (., p_n) for this problem
     double *Tq = Tp + NPAD;                             // [NPAD] targets of the pairs (., q_n)
     double *Hc2 = Tq + NPAD;                            // [NPAD] 2 act (d - T) of the second terms around the hub node
-    double *RS = Hc2 + NPAD;                            // [kSlices][NPAD] slices' partial sums of c2 over the clique pairs
-    double *momS = RS + kSlices * NPAD;                  // [kMom] moments (block-uniform values kept out of the registers)
+    double *RS = Hc2 + NPAD;                            // [kWarps][NPAD] slices' partial sums of c2 over the clique pairs
+    double *momS = RS + kWarps * NPAD;                  // [kMom] moments (block-uniform values kept out of the registers)
     double *XW = momS + kMom;                           // [NPAD] <X_j, delta_j> of the clique nodes
-    double *ZH = XW + NPAD;                             // [4] reaction on the hub node from the worker warps' tile nodes
-    double *goal = ZH + 4;                              // [n_goal]
+    double *goal = XW + NPAD;                           // [n_goal]
     int *s_b = reinterpret_cast<int *>(goal + ((a.n_goal + 1) & ~1));                    // [0] work item, [1] park slot
     unsigned long long *s_t = reinterpret_cast<unsigned long long *>(s_b + 2);          // [0] problem start, [1] elapsed
     const int gp = tb.gp, gq = tb.gq;
     const int jF = tb.jF, mF = tb.mF;
-    const bool has_fast = mF < NB;      // then MS == mF: the worker warps' blocks are the clique blocks
+    const bool has_fast = mF < NB;
     const int node = owner ? tb.perm[tid] : 0;          // thread tid owns POSITION tid = node perm[tid]
     const bool in_clique = owner && tid >= jF;
     const bool fast_owner = owner && tid >= 32 * mF;     // its pairs with the clique go through the moments
@@ -194,47 +178,45 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
     for (int e = tid; e < NPAD; e += kThreads) Hc2[e] = 0.0;
     __syncthreads();
 
-    double xt[NT][3];           // 2 * coordinates of this lane's tile nodes (blocks mbase + m) at the cached point
-    unsigned long long amask[NT];   // bit jj: term (tile node m, neighbour jlo + jj) active there
+    double xt[NB][3];           // 2 * coordinates of this lane's tile nodes at the cached point
+    unsigned long long amask[NB];   // bit jj: term (tile node m, neighbour jlo + jj) active there
     uint32_t hact = 0u;         // bit m: second term of the pair (tile node m, hub) active there (hub's slice only)
     const int hub = tb.hub;
     const bool hub_warp = hub >= jlo && hub < jhi;   // this warp's slice contains the hub neighbour
     // c2(i = lane + 32 m, j) in the packed cache is a row entry of block (m, jb) when m <= jb and a column
     // entry of block (jb, m) otherwise; padding lanes of a ragged last block re-read its last row
-    int col_off[NT];
+    int col_off[NB];
 #pragma unroll
-    for (int m = 0; m < NT; ++m) {
-        const int mb = min(mbase + m, NB - 1);
-        col_off[m] = 16 * mb * (mb + 1) * kStride + min(lane, c2_rows(N, mb) - 1) * kStride;
+    for (int m = 0; m < NB; ++m) {
+        col_off[m] = 16 * m * (m + 1) * kStride + min(lane, c2_rows(N, m) - 1) * kStride;
         amask[m] = 0ull;
     }
-    // offsets / strides of the reads of this lane's TC tile blocks for the neighbours j0, j0 + 1, ... inside block jb
-    auto c2_walk = [&](int jb, int j0, int (&off)[NT], int (&step)[NT]) {
+    // offsets / strides of the NB reads for the neighbours j0, j0 + 1, ... inside block jb
+    auto c2_walk = [&](int jb, int j0, int (&off)[NB], int (&step)[NB]) {
         const int jl = j0 & 31;
         const int rows_jb = c2_rows(N, jb);
 #pragma unroll
-        for (int m = 0; m < TC; ++m) {
-            const int mb = mbase + m;
-            const bool row = mb <= jb;
-            off[m] = row ? c2_base(N, 0, jb) + (mb * rows_jb + jl) * kStride + lane
-                         : col_off[m] + jb * c2_rows(N, mb) * kStride + jl;
+        for (int m = 0; m < NB; ++m) {
+            const bool row = m <= jb;
+            off[m] = row ? c2_base(N, 0, jb) + (m * rows_jb + jl) * kStride + lane
+                         : col_off[m] + jb * c2_rows(N, m) * kStride + jl;
             step[m] = row ? kStride : 1;
         }
     };
 
-    auto load_tile = [&](const double *buf, double (&t)[NT][3]) {
+    auto load_tile = [&](const double *buf, double (&t)[NB][3]) {
 #pragma unroll
-        for (int m = 0; m < TC; ++m) {
-            t[m][0] = buf[lane + 32 * (mbase + m)];
-            t[m][1] = buf[NPAD + lane + 32 * (mbase + m)];
-            t[m][2] = buf[2 * NPAD + lane + 32 * (mbase + m)];
+        for (int m = 0; m < NB; ++m) {
+            t[m][0] = buf[lane + 32 * m];
+            t[m][1] = buf[NPAD + lane + 32 * m];
+            t[m][2] = buf[2 * NPAD + lane + 32 * m];
         }
     };
-    auto store_partials = [&](const double (&z)[NT][3]) {
+    auto store_partials = [&](const double (&z)[NB][3]) {
 #pragma unroll
-        for (int m = 0; m < TC; ++m) {
+        for (int m = 0; m < NB; ++m) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) Zp[(slice * 3 + q) * NPAD + lane + 32 * (mbase + m)] = z[m][q];
+            for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + lane + 32 * m] = z[m][q];
         }
     };
     // owner: sum of the slices' partial sums of its node, in slice order
@@ -243,8 +225,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
         for (int q = 0; q < 3; ++q) {
             double acc = Zp[q * NPAD + tid];
 #pragma unroll
-            for (int w = 1; w < kSlices; ++w) acc += Zp[(w * 3 + q) * NPAD + tid];
-            if (tid == hub) acc -= ZH[q];      // second terms seen from the worker warps' tile nodes
+            for (int w = 1; w < kWarps; ++w) acc += Zp[(w * 3 + q) * NPAD + tid];
             z[q] = acc;
         }
     };
@@ -264,8 +245,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
     // between barriers (1) and (2), next to the pair pass; nothing rides on the latency chain of the iteration.
     auto direction_moments = [&]() {
         {
-            const int t2 = tid - kOwnWarps * 32;                       // the worker warps form the moments
-            const int k = t2 < 120 ? t2 >> 3 : 14, part = t2 & 7;      // their last eight threads repeat moment 14 and drop it
+            const int k = tid < 120 ? tid >> 3 : 14, part = tid & 7;   // the last eight threads repeat moment 14 and drop it
             const double *A = k < 3 ? nullptr : P2 + (k < 12 ? (k - 3) / 3 : k - 12) * NPAD;
             const double *Bv = k < 3 ? V + k * NPAD : (k < 12 ? V + ((k - 3) % 3) * NPAD : XW);
             double s0 = 0.0, s1 = 0.0;
@@ -279,31 +259,29 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 1);
             sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 2);
             sm += __shfl_xor_sync(GIK_FULL_MASK, sm, 4);
-            if (part == 0 && t2 < 120) momS[k] = sm;
+            if (part == 0 && tid < 120) momS[k] = sm;
         }
     };
 
     // costs.py:125-169 at the point published (doubled) in P2: rebuilds xt, C2 and the activity mask, leaves the
-    // slices' partial half-gradients in Zp and the warps' cost shares in redF.  Caller synchronises before and after.
-    // TC = tile blocks of this warp's role (compile time: the unrolled tile loops carry no guards).
+    // slices' partial half-gradients in Zp and their cost shares in redF.  Caller synchronises before and after.
     auto pair_pass_cost = [&]() {
-        const bool role_fast = role == 1 && has_fast;
         load_tile(P2, xt);
-        double gpart[NT][3], rsum[NT];
+        double gpart[NB][3], rsum[NB];
         double fpart = 0.0;
 #pragma unroll
-        for (int m = 0; m < TC; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; amask[m] = 0ull; rsum[m] = 0.0; }
+        for (int m = 0; m < NB; ++m) { gpart[m][0] = 0.0; gpart[m][1] = 0.0; gpart[m][2] = 0.0; amask[m] = 0ull; rsum[m] = 0.0; }
         for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
             const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
-            int off[NT], step[NT];
+            int off[NB], step[NB];
             c2_walk(jb, j0, off, step);
             for (int j = j0; j < j1; ++j) {
                 const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
                 const unsigned long long bit = 1ull << (j - jlo);
-                const bool fj = role_fast && j >= jF;
+                const bool fj = j >= jF;
 #pragma unroll
-                for (int m = 0; m < TC; ++m) {
-                    const int i = lane + 32 * (mbase + m);
+                for (int m = 0; m < NB; ++m) {
+                    const int i = lane + 32 * m;
                     const unsigned kind = i < N ? tb.kind[(size_t)j * N + i] : 3u;
                     const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;   // 2 (x_i - x_j)
                     const double d4 = dx * dx + dy * dy + dz * dz;                               // 4 d_ij
@@ -318,9 +296,9 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
                     gpart[m][0] = fma(rr, dx, gpart[m][0]);      // 2 r (x_i - x_j)
                     gpart[m][1] = fma(rr, dy, gpart[m][1]);
                     gpart[m][2] = fma(rr, dz, gpart[m][2]);
-                    if (mbase + m <= jb) C2[off[m]] = 2.0 * rr;  // the mirrored pair computes the same bits
+                    if (m <= jb) C2[off[m]] = 2.0 * rr;          // the mirrored pair computes the same bits
                     off[m] += step[m];
-                    if (fj) rsum[m] += 2.0 * rr;                 // clique pair: its c2 w term is split (pair_pass_hess)
+                    if (fj && m >= mF) rsum[m] += 2.0 * rr;      // clique pair: its c2 w term is split (pair_pass_hess)
                     amask[m] |= act ? bit : 0ull;
                 }
             }
@@ -333,8 +311,8 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             double fh = 0.0;
             hact = 0u;
 #pragma unroll
-            for (int m = 0; m < TC; ++m) {
-                const int i = lane + 32 * (mbase + m);
+            for (int m = 0; m < NB; ++m) {
+                const int i = lane + 32 * m;
                 const int ic = min(i, N - 1);
                 const unsigned kind = i < N ? tb.hub_kind[i] : 3u;
                 const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
@@ -350,7 +328,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
                 react[0] = fma(rr, dx, react[0]);
                 react[1] = fma(rr, dy, react[1]);
                 react[2] = fma(rr, dz, react[2]);
-                if (i < N) Hc2[i] = 2.0 * rr;
+                Hc2[i] = 2.0 * rr;
                 hact |= act ? (1u << m) : 0u;
             }
             fpart = fma(2.0, fh, fpart);
@@ -361,20 +339,15 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             }
         }
         store_partials(gpart);
-        if (role_fast) {
+        if (has_fast) {
 #pragma unroll
-            for (int m = 0; m < TC; ++m) RS[slice * NPAD + lane + 32 * (mbase + m)] = rsum[m];
+            for (int m = 0; m < NB; ++m) RS[warp * NPAD + lane + 32 * m] = rsum[m];
         }
         if (hub_warp) {
-            // the hub is a free node: its column of Zp belongs to the OWNER warp of this slice, which subtracts its
-            // reaction there; the worker warp leaves its reaction in ZH for the hub's owner thread (gather)
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (role == 0) Zp[(slice * 3 + q) * NPAD + hub] -= react[q];
-                    else ZH[q] = react[q];
-                }
+                for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + hub] -= react[q];
             }
         }
         double f1[1] = {0.5 * fpart};   // every undirected term is seen from both ends
@@ -383,47 +356,55 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
 
     // costs.py:171-207 at the cached point along the direction published in V: partial sums into Zp
     auto pair_pass_hess = [&]() {
-        double wt[NT][3], z[NT][3];
+        double wt[NB][3], z[NB][3];
         load_tile(V, wt);
 #pragma unroll
-        for (int m = 0; m < TC; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
-        const bool role_fast = role == 1 && has_fast;
-        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
-            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
-            int off[NT], step[NT];
-            c2_walk(jb, j0, off, step);
-            unsigned long long bit = 1ull << (j0 - jlo);
-            const int jm = role_fast ? min(max(j0, jF), j1) : j1;     // [j0, jm): full evaluation, [jm, j1): clique pairs
+        for (int m = 0; m < NB; ++m) { z[m][0] = 0.0; z[m][1] = 0.0; z[m][2] = 0.0; }
+        // neighbours [ja, jb2) of one 32-node block; MF = first tile block whose pairs with these neighbours lie inside
+        // the equality clique (compile-time, so that the unrolled tile loop has no branches): for those only
+        // -c2_ij delta_j is accumulated here -- (sum_j c2_ij) delta_i and the <D,w> D part (15 moments of delta over the
+        // clique) are added by the node's owner
+        auto hess_range = [&](auto mf_tag, int ja, int jb2, int (&off)[NB], const int (&step)[NB], unsigned long long &bit) {
+            constexpr int MF = decltype(mf_tag)::value;
 #pragma unroll 2
-            for (int j = j0; j < jm; ++j) {
-                const double px = P2[j], py = P2[NPAD + j], pz = P2[2 * NPAD + j];
+            for (int j = ja; j < jb2; ++j) {
                 const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
+                double px = 0.0, py = 0.0, pz = 0.0;
+                if (MF > 0) { px = P2[j]; py = P2[NPAD + j]; pz = P2[2 * NPAD + j]; }
 #pragma unroll
-                for (int m = 0; m < TC; ++m) {
+                for (int m = 0; m < NB; ++m) {
                     const double c2 = C2[off[m]];
                     off[m] += step[m];
-                    const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
-                    const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
-                    double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
-                    s = (amask[m] & bit) ? s : 0.0;
-                    z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
-                    z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
-                    z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                    if (m >= MF) {
+                        z[m][0] = fma(-c2, vx, z[m][0]);
+                        z[m][1] = fma(-c2, vy, z[m][1]);
+                        z[m][2] = fma(-c2, vz, z[m][2]);
+                    } else {
+                        const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
+                        const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
+                        double s = dx * wx + dy * wy + dz * wz;                  // 2 <D, w>
+                        s = (amask[m] & bit) ? s : 0.0;
+                        z[m][0] = fma(s, dx, fma(c2, wx, z[m][0]));              // 4 <D,w> D + 2 r w
+                        z[m][1] = fma(s, dy, fma(c2, wy, z[m][1]));
+                        z[m][2] = fma(s, dz, fma(c2, wz, z[m][2]));
+                    }
                 }
                 bit <<= 1;
             }
-            // pairs inside the equality clique: only -c2_ij delta_j here -- (sum_j c2_ij) delta_i and the <D,w> D part
-            // (15 moments of delta over the clique) are added by the node's owner
-#pragma unroll 2
-            for (int j = jm; j < j1; ++j) {
-                const double vx = V[j], vy = V[NPAD + j], vz = V[2 * NPAD + j];
-#pragma unroll
-                for (int m = 0; m < TC; ++m) {
-                    const double c2 = C2[off[m]];
-                    off[m] += step[m];
-                    z[m][0] = fma(-c2, vx, z[m][0]);
-                    z[m][1] = fma(-c2, vy, z[m][1]);
-                    z[m][2] = fma(-c2, vz, z[m][2]);
+        };
+        for (int jb = jlo >> 5; jb <= (jhi - 1) >> 5; ++jb) {
+            const int j0 = max(jlo, 32 * jb), j1 = min(jhi, 32 * jb + 32);
+            int off[NB], step[NB];
+            c2_walk(jb, j0, off, step);
+            unsigned long long bit = 1ull << (j0 - jlo);
+            const int jm = has_fast ? min(max(j0, jF), j1) : j1;     // [j0, jm): no clique neighbour, [jm, j1): clique
+            hess_range(std::integral_constant<int, NB>(), j0, jm, off, step, bit);
+            if (jm < j1) {
+                switch (mF) {
+                    case 0: hess_range(std::integral_constant<int, 0>(), jm, j1, off, step, bit); break;
+                    case 1: hess_range(std::integral_constant<int, (1 < NB ? 1 : NB)>(), jm, j1, off, step, bit); break;
+                    case 2: hess_range(std::integral_constant<int, (2 < NB ? 2 : NB)>(), jm, j1, off, step, bit); break;
+                    default: hess_range(std::integral_constant<int, (3 < NB ? 3 : NB)>(), jm, j1, off, step, bit); break;
                 }
             }
         }
@@ -432,8 +413,8 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             const double px = P2[hub], py = P2[NPAD + hub], pz = P2[2 * NPAD + hub];
             const double vx = V[hub], vy = V[NPAD + hub], vz = V[2 * NPAD + hub];
 #pragma unroll
-            for (int m = 0; m < TC; ++m) {
-                const double c2 = Hc2[min(lane + 32 * (mbase + m), NPAD - 1)];
+            for (int m = 0; m < NB; ++m) {
+                const double c2 = Hc2[lane + 32 * m];
                 const double dx = xt[m][0] - px, dy = xt[m][1] - py, dz = xt[m][2] - pz;
                 const double wx = wt[m][0] - vx, wy = wt[m][1] - vy, wz = wt[m][2] - vz;
                 double s = dx * wx + dy * wy + dz * wz;
@@ -453,10 +434,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (role == 0) Zp[(slice * 3 + q) * NPAD + hub] -= react[q];
-                    else ZH[q] = react[q];
-                }
+                for (int q = 0; q < 3; ++q) Zp[(warp * 3 + q) * NPAD + hub] -= react[q];
             }
         }
     };
@@ -471,7 +449,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
     auto gather_rs = [&]() -> double {
         double acc = RS[tid];
 #pragma unroll
-        for (int w = 1; w < kSlices; ++w) acc += RS[w * NPAD + tid];
+        for (int w = 1; w < kWarps; ++w) acc += RS[w * NPAD + tid];
         return acc;
     };
     // owner of a node whose clique pairs took the fast path: Z_i += sum_j (X_i - X_j)(X_i - X_j)^T (w_i - w_j) over the clique
@@ -550,7 +528,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             const double X[3] = {2.0 * x[0], 2.0 * x[1], 2.0 * x[2]};
             double cc[9];
             clique_consts(X, in_clique, cc);
-            if (ROLE == 0) warp_sum_store<9>(cc, redB + warp * kRedB, first_of_own_warp);
+            warp_sum_store<9>(cc, redB + warp * kRedB, first_of_own_warp);
             __syncthreads();
             if (tid < 9) {          // the sum block_sum_load forms, without indexing a register array by tid
                 double sm = redB[tid];
@@ -578,7 +556,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
             // threads without a node carry zeros in all node state, so every warp can run the butterflies
             double v[7] = {g[0] * g[0] + g[1] * g[1] + g[2] * g[2],
                            x[0] * x[0], x[0] * x[1], x[0] * x[2], x[1] * x[1], x[1] * x[2], x[2] * x[2]};
-            if (ROLE == 0) warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
+            warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
             __syncthreads();
             block_sum_load<7, kRedA>(v, redA);
             fx = total_cost();
@@ -629,7 +607,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
                     v[4] = dl[1] * x[2] - dl[2] * x[1];                // u = sum delta_i x Y_i
                     v[5] = dl[2] * x[0] - dl[0] * x[2];
                     v[6] = dl[0] * x[1] - dl[1] * x[0];
-                    if (ROLE == 0) warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
+                    warp_sum_store<7>(v, redA + warp * kRedA, first_of_own_warp);
                     __syncthreads();                                   // (3)
                     block_sum_load<7, kRedA>(v, redA);
                     double om[3];
@@ -667,7 +645,7 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
                             sdot[1] = fma(ne[q], nh[q], sdot[1]);
                             sdot[2] = fma(nr[q], nr[q], sdot[2]);
                         }
-                        if (ROLE == 0) warp_sum_store<3>(sdot, redB + warp * kRedB, first_of_own_warp);
+                        warp_sum_store<3>(sdot, redB + warp * kRedB, first_of_own_warp);
                     }
                     __syncthreads();                                   // (4)
                     double sd[3];
@@ -715,11 +693,11 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
                 if (has_fast) {
                     const double X[3] = {2.0 * dl[0], 2.0 * dl[1], 2.0 * dl[2]};
                     clique_consts(X, in_clique, v + 9);
-                    if (ROLE == 0) warp_sum_store<18>(v, redA + warp * kRedA, first_of_own_warp);
+                    warp_sum_store<18>(v, redA + warp * kRedA, first_of_own_warp);
                     __syncthreads();
                     block_sum_load<18, kRedA>(v, redA);
                 } else {
-                    if (ROLE == 0) warp_sum_store<9>(v, redA + warp * kRedA, first_of_own_warp);
+                    warp_sum_store<9>(v, redA + warp * kRedA, first_of_own_warp);
                     __syncthreads();
                     block_sum_load<9, kRedA>(v, redA);
                 }
@@ -810,27 +788,20 @@ __device__ __forceinline__ void cta_body(const RtrArgs &a, const CtaTables &tb)
     }
 }
 
-template <int NB, int MS>
-__global__ void __launch_bounds__(kThreads, 2) k_rtr_cta(const RtrArgs a, const CtaTables tb)
-{
-    if (threadIdx.x < kOwnWarps * 32) cta_body<NB, MS, 0>(a, tb);
-    else cta_body<NB, MS, 1>(a, tb);
-}
-
 size_t cta_smem_bytes(int N, int n_goal)
 {
     const int goal_pad = (n_goal + 1) & ~1;
-    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kSlices + 3 + kSlices + 1) * NPAD + kMom + 4 + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
+    size_t smem = ((size_t)c2_doubles(N) + (6 + 3 * kWarps + 3 + kWarps + 1) * NPAD + kMom + kOwnWarps * (kRedA + kRedB) + kWarps + goal_pad) *
                       sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned long long);
     return (smem + 15) & ~(size_t)15;
 }
 
 }  // namespace
 
-template <int NB, int MS>
+template <int NB>
 static int launch_cta(const GikPlan *p, RtrArgs &a, const CtaTables &tb, size_t smem, cudaStream_t st)
 {
-    auto kern = k_rtr_cta<NB, MS>;
+    auto kern = k_rtr_cta<NB>;
     static size_t cached_smem = ~(size_t)0;
     static int cached_per_sm = 0, cached_dev = -1;
     if (cached_smem != smem || cached_dev != p->device) {
@@ -865,21 +836,14 @@ int gik_launch_rtr_cta(const GikPlan *p, RtrArgs &a, cudaStream_t st)
     tb.gq = p->n_dense_goal > 0 ? p->dense_goal_q : -1;
     tb.perm = p->dense_perm;
     tb.jF = p->dense_clique_start;
-    const int NB = (N + 31) / 32;
-    tb.mF = (p->dense_clique_start + 31) / 32;      // first 32-node block that lies inside the clique ...
-    if (tb.mF < 1) tb.mF = 1;                       // ... but block 0 always takes the full pair evaluation
-    if (tb.mF > NB) tb.mF = NB;
-    // blocks of the owner warps: the non-clique blocks, or half of the blocks when there is no clique
-    const int MS = tb.mF < NB ? tb.mF : (NB + 1) / 2;
+    tb.mF = (p->dense_clique_start + 31) / 32;      // first 32-node block that lies inside the clique
+    if (tb.mF > (N + 31) / 32) tb.mF = (N + 31) / 32;
     tb.hub = p->dense_hub;
     tb.hub_kind = p->dense_hub_kind;
     tb.hub_target = p->dense_hub_target;
-    switch (NB * 10 + MS) {
-        case 21: return launch_cta<2, 1>(p, a, tb, smem, st);
-        case 31: return launch_cta<3, 1>(p, a, tb, smem, st);
-        case 32: return launch_cta<3, 2>(p, a, tb, smem, st);
-        case 41: return launch_cta<4, 1>(p, a, tb, smem, st);
-        case 42: return launch_cta<4, 2>(p, a, tb, smem, st);
-        default: return launch_cta<4, 3>(p, a, tb, smem, st);
+    switch ((N + 31) / 32) {
+        case 2: return launch_cta<2>(p, a, tb, smem, st);
+        case 3: return launch_cta<3>(p, a, tb, smem, st);
+        default: return launch_cta<4>(p, a, tb, smem, st);
     }
 }
