@@ -282,6 +282,7 @@ __device__ __noinline__ void ql_implicit(double *d, double *e, int n, double *W,
 // W[:, c] <- H_0 H_1 ... H_{n-3} W[:, c] for the columns c = cols[0..ncols): eigenvectors of the tridiagonal ->
 // eigenvectors of the matrix `tridiagonalize` reduced.  No CTA barriers: one thread per column when there are many
 // columns, one warp per column (lanes over the rows, butterfly for the dot product) when there are few.
+template <int ROWS>   // rows per lane of the warp-per-column variant: n <= 32 ROWS + 1
 __device__ __noinline__ void apply_reflectors(const double *A, int n, int ld, const double *tau, double *W, int ldw, const int *cols,
                                  int ncols)
 {
@@ -296,9 +297,10 @@ __device__ __noinline__ void apply_reflectors(const double *A, int n, int ld, co
                 const int m = n - k - 1;
                 const double *v = A + (k + 1) * ld + k;
                 double *w = W + (k + 1) * ldw + c;
-                double vr[4], wr[4], t = 0.0;     // m <= 127: at most four rows per lane
+                double vr[ROWS], wr[ROWS], t = 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < ROWS; ++u) {
+                    if (ROWS > 4 && 32 * u >= m) break;
                     const int j = lane + 32 * u;
                     vr[u] = j < m ? v[j * ld] : 0.0;
                     wr[u] = j < m ? w[j * ldw] : 0.0;
@@ -308,7 +310,8 @@ __device__ __noinline__ void apply_reflectors(const double *A, int n, int ld, co
                 for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(GIK_FULL_MASK, t, off);
                 t *= -beta;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < ROWS; ++u) {
+                    if (ROWS > 4 && 32 * u >= m) break;
                     const int j = lane + 32 * u;
                     if (j < m) w[j * ldw] = fma(t, vr[u], wr[u]);
                 }
@@ -378,7 +381,8 @@ __device__ int sturm_count_above(const double *d, const double *e, int n, double
     return n - below;
 }
 
-// TS = 4 x 4 register tiles per thread (TS * blockDim.x >= ceil(N / 4)^2), MAXT / MINB = launch bounds: the kernel is
+// TS = 4 x 4 register tiles per thread (TS * blockDim.x >= ceil(N / 4)^2; 0: none, looped fallback for N > 128),
+// MAXT / MINB = launch bounds: the kernel is
 // latency bound (one thread runs the QL recurrence while the CTA waits), so resident CTAs per SM are what counts.
 template <int TS, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_bounds_init(const BiArgs a)
@@ -436,10 +440,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_bounds_init(const BiArgs a)
             // min-plus closure (Floyd-Warshall) with the matrix in register tiles.  Step k needs row k only (the matrix
             // stays symmetric bit for bit: u_ik + u_kj and u_jk + u_ki add the same two numbers), which its owners
             // publish after step k - 1; row k is a fixed point of step k.
-            {
-                double U[TS][4][4];
-                int i0[TS], j0[TS];
-                bool valid[TS];
+            if (TS == 0) {
+                // graphs too large for register tiles (N > 128): the plain in-place iteration, thread = (column, row group)
+                for (int k = 0; k < N; ++k) {
+                    for (int i = tg; i < N; i += G) {
+                        const double uik = Up[i * N + k];
+                        for (int j = tj; j < N; j += TJ) Up[i * N + j] = dmin(Up[i * N + j], uik + Up[k * N + j]);
+                    }
+                    __syncthreads();
+                }
+            } else {
+                constexpr int TSA = TS > 0 ? TS : 1;
+                double U[TSA][4][4];
+                int i0[TSA], j0[TSA];
+                bool valid[TSA];
 #pragma unroll
                 for (int ts = 0; ts < TS; ++ts) {
                     const int t = tid + ts * nt;
@@ -531,8 +545,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_bounds_init(const BiArgs a)
             }
             __syncthreads();
             // second product in 4 x 4 register tiles (edge tiles compute on clamped indices and drop the duplicates)
+            const int tile_rounds = TS > 0 ? TS : (ntiles + nt - 1) / nt;   // (no accumulator outlives a tile here)
 #pragma unroll 1
-            for (int ts = 0; ts < TS; ++ts) {
+            for (int ts = 0; ts < tile_rounds; ++ts) {
                 const int t = tid + ts * nt;
                 if (t >= ntiles) break;
                 const int u0 = (t / NT4) * 4, v0 = (t % NT4) * 4;
@@ -633,7 +648,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_bounds_init(const BiArgs a)
         rank_desc(dd, N, rank, order);
         for (int i = tid; i < N; i += nt) { lam[i] = dd[i]; if (!(dd[i] > lcut)) rank[i] = N; }
         __syncthreads();
-        apply_reflectors(G, N, N, tau, V, N, order, npos);
+        apply_reflectors<(TS == 0 ? 15 : 4)>(G, N, N, tau, V, N, order, npos);
         __syncthreads();
         BI_TICK("backtr");
         // Eigenvector signs are arbitrary, yet the rank heuristic below is NOT invariant to them
@@ -718,7 +733,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_bounds_init(const BiArgs a)
             tridiagonalize(S, K, K, dd, ee, tau, hv, part, red, par);
             ql_implicit(dd, ee, K, E, K, rot, meta);
             rank_desc(dd, K, rank, order);
-            apply_reflectors(S, K, K, tau, E, K, order, K < 3 ? K : 3);   // only the three leading eigenvectors are used
+            apply_reflectors<(TS == 0 ? 15 : 4)>(S, K, K, tau, E, K, order, K < 3 ? K : 3);   // only the three leading eigenvectors are used
             __syncthreads();
         }
         BI_TICK("eig_proj");
@@ -759,7 +774,7 @@ int launch(const GikPlan *p, BiArgs &a, void *workspace, cudaStream_t st)
     const size_t mat = (size_t)N * N * sizeof(double);
     size_t smem = small_bytes(N) + (p->bi_mode == 0 ? 3 : (p->bi_mode == 1 ? 2 : 0)) * mat;
     const int variant = gik_bi_variant(N);
-    const int threads = variant == 0 ? 32 : (variant == 3 ? 512 : 128);
+    const int threads = variant == 0 ? 32 : (variant >= 3 ? 512 : 128);
     int blocks = a.B;
     a.use_scratch = p->bi_mode;
     a.scratch = static_cast<double *>(workspace);
@@ -769,7 +784,8 @@ int launch(const GikPlan *p, BiArgs &a, void *workspace, cudaStream_t st)
         return GIK_EINVAL;
     }
     void (*kern)(const BiArgs) = variant == 0 ? k_bounds_init<1, 32, 24> : (variant == 1 ? k_bounds_init<1, 128, 6> :
-                                 (variant == 2 ? k_bounds_init<2, 128, 4> : k_bounds_init<2, 512, 1>));
+                                 (variant == 2 ? k_bounds_init<2, 128, 4> : (variant == 3 ? k_bounds_init<2, 512, 1> :
+                                                                              k_bounds_init<0, 512, 1>)));
     // shared-memory opt-in and occupancy depend on (device, N) only: looked up once per plan geometry
     static int cached_dev = -1, cached_N = -1, cached_mode = -1, cached_cap = 0;
     if (cached_dev != p->device || cached_N != N || cached_mode != p->bi_mode) {

@@ -314,7 +314,9 @@ int dispatch_costs(const GikPlan *p, const double *Y, const double *Wd, const do
     switch (p->NPL) {
         case 1: return launch_costs<32, 1, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
         case 2: return launch_costs<32, 2, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
-        default: return launch_costs<32, 4, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        case 4: return launch_costs<32, 4, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        case 8: return launch_costs<32, 8, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        default: return launch_costs<32, 15, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
     }
 }
 
@@ -378,11 +380,13 @@ extern "C" int gik_proj(int32_t N, const double *Y, const double *Z, int32_t B, 
 {
     if (B == 0) return GIK_OK;
     if (!Y || !Z || !out || B < 0 || N < 2) { gik_set_error("gik_proj: bad argument"); return GIK_EINVAL; }
-    if (N > 128) { gik_set_error("gik_proj: N=%d exceeds the compiled limit of 128", N); return GIK_ELIMIT; }
+    if (N > 480) { gik_set_error("gik_proj: N=%d exceeds the compiled limit of 480", N); return GIK_ELIMIT; }
     if (B == 0) return GIK_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 16) return launch_proj<16, 1>(N, Y, Z, B, out, st);
     if (N <= 32) return launch_proj<32, 1>(N, Y, Z, B, out, st);
     if (N <= 64) return launch_proj<32, 2>(N, Y, Z, B, out, st);
-    return launch_proj<32, 4>(N, Y, Z, B, out, st);
+    if (N <= 128) return launch_proj<32, 4>(N, Y, Z, B, out, st);
+    if (N <= 256) return launch_proj<32, 8>(N, Y, Z, B, out, st);
+    return launch_proj<32, 15>(N, Y, Z, B, out, st);
 }

@@ -115,8 +115,10 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
     else if (N <= 32) { p->W = 32; p->NPL = 1; }
     else if (N <= 64) { p->W = 32; p->NPL = 2; }
     else if (N <= 128) { p->W = 32; p->NPL = 4; }
+    else if (N <= 256) { p->W = 32; p->NPL = 8; }    // generic kernels only; part of the per-lane state in local memory
+    else if (N <= 480) { p->W = 32; p->NPL = 15; }
     else {
-        gik_set_error("gik_plan_create: n_nodes=%d exceeds the compiled limit of 128", N);
+        gik_set_error("gik_plan_create: n_nodes=%d exceeds the compiled limit of 480", N);
         delete p;
         return GIK_ELIMIT;
     }
@@ -397,7 +399,7 @@ extern "C" int gik_plan_create(const GikPlanDesc *d, GikPlan **out)
         if (occ0 > regs) occ0 = regs;
         if (occ1 > regs) occ1 = regs;
         p->bi_mode = (occ0 >= 1 && occ0 >= occ1) ? 0 : (occ1 >= 1 ? 1 : 2);
-        p->bi_blocks = p->bi_mode == 1 ? p->sm_count * occ1 : 2 * p->sm_count;
+        p->bi_blocks = p->bi_mode == 1 ? p->sm_count * occ1 : p->sm_count * (regs < 2 ? regs : 2);
     }
 
     bool ok = true;

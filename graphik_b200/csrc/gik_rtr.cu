@@ -458,7 +458,10 @@ static int rtr_dispatch(const GikPlan *p, RtrArgs &a, bool sliced, cudaStream_t 
     switch (p->NPL) {
         case 1: return launch_rtr<32, 1>(p, a, st);
         case 2: return launch_rtr<32, 2>(p, a, st);
-        default: return launch_rtr<32, 4>(p, a, st);
+        case 4: return launch_rtr<32, 4>(p, a, st);
+        case 8: return launch_rtr<32, 8>(p, a, st);    // 129 .. 256 nodes: the state no longer fits the register file; the
+                                                         // compiler keeps part of it in (L1-cached) local memory
+        default: return launch_rtr<32, 15>(p, a, st);  // .. 480 nodes
     }
 }
 

@@ -128,7 +128,8 @@ typedef struct {
 #define GIK_KERNEL_LATENCY 1     /* one warp per problem: register slot cache (N <= 32), two nodes per lane with a
                                     shared-memory slot cache (32 < N <= 64) */
 #define GIK_KERNEL_THROUGHPUT 2  /* two problems per warp (N <= 16); bit-identical to GIK_KERNEL_LATENCY */
-#define GIK_KERNEL_GENERIC 3     /* W-lane groups, any N <= 128 */
+#define GIK_KERNEL_GENERIC 3     /* W-lane groups, any N <= 480 (beyond 128 nodes part of the per-lane state lives in
+                                    local memory: a fallback, several times slower per node pair) */
 #define GIK_KERNEL_DENSE 4       /* one CTA per problem, two CTAs per SM, packed symmetric pair cache in shared
                                     memory (32 < N <= 128) */
 

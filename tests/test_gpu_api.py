@@ -136,7 +136,7 @@ def test_c_abi_error_codes_and_empty_batches():
     assert L.gik_rtr_solve(h, null, null, 4, None, null, null, null, null, null, null, null, 0, null, null) == -1
     assert L.gik_proj(1, null, null, 4, null, null) == -1
     # more nodes than any kernel is compiled for -> GIK_ELIMIT (-3) at plan creation
-    N = 200
+    N = 500
     with pytest.raises(_lib.GikError, match="exceeds the compiled limit"):
         Plan.from_matrices(np.ones((N, N)), np.triu(np.ones((N, N)), 1))
     # a plan without joint tables refuses joint recovery instead of reading garbage

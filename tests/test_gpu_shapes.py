@@ -28,7 +28,7 @@ def _random_dh_chain(n, seed):
     return robot, ProblemGraphRevolute(robot)
 
 
-def _check_against_group_kernel_and_oracle(robot, graph, kernel, B=4, maxiter=40, seed=3):
+def _check_against_group_kernel_and_oracle(robot, graph, kernel, B=4, maxiter=40, seed=3, has_other_kernel=True):
     from graphik_b200.engine import BatchIK, make_opts
     from oracle import oracle as orc
     eng = BatchIK(graph)
@@ -45,7 +45,8 @@ def _check_against_group_kernel_and_oracle(robot, graph, kernel, B=4, maxiter=40
     tr, tg = out["trace"].cpu().numpy(), gen["trace"].cpu().numpy()
     assert np.array_equal(tr[:, :4][:, :, [1, 2, 4]], tg[:, :4][:, :, [1, 2, 4]]), (tr[:, :4], tg[:, :4])
     np.testing.assert_allclose(tr[:, :4, 3], tg[:, :4, 3], rtol=1e-6)
-    assert not np.array_equal(tr[:, :8, 3], tg[:, :8, 3]), "the requested kernel fell back to the group kernel"
+    if has_other_kernel:
+        assert not np.array_equal(tr[:, :8, 3], tg[:, :8, 3]), "the requested kernel fell back to the group kernel"
     gdh, Y0h = gd.cpu().numpy(), Y0.cpu().numpy()
     x, fx = out["x"].cpu().numpy(), out["f(x)"].cpu().numpy()
     gs = a["goal_slot"]
@@ -83,3 +84,27 @@ def test_dense_kernel_at_block_boundaries(n_obstacles, semantics):
         graph.add_spherical_obstacle("o%d" % k, c, r)
     assert graph.number_of_nodes() == 18 + n_obstacles
     _check_against_group_kernel_and_oracle(robot, graph, "dense", B=3, maxiter=30)
+
+
+@pytest.mark.parametrize("n_height,n_width", [(12, 10), (14, 12), (18, 16)])
+def test_graphs_above_128_nodes(n_height, n_width):
+    """Beyond the dense kernel's 128 nodes (table_environment() with a finer grid: N = 166 / 218 / 346, reference
+    utils.py:179-191): the group kernels with eight / fifteen nodes per lane, bound smoothing without register tiles and all three
+    matrices in the caller's workspace.  Whole device pipeline against the oracle, as for the other shapes, plus the
+    bounds against the oracle's bound_smoothing on one goal."""
+    from oracle import oracle as orc
+    from graphik_b200.utils.utils import table_environment
+    robot, graph = load_robot("kuka")
+    for k, (c, r) in enumerate(table_environment(n_height=n_height, n_width=n_width)):
+        graph.add_spherical_obstacle("o%d" % k, c, r)
+    N = graph.number_of_nodes()
+    assert 128 < N <= 480
+    eng = _check_against_group_kernel_and_oracle(robot, graph, "auto", B=2, maxiter=12, has_other_kernel=False)
+    assert eng.plan.N == N
+    rng = np.random.RandomState(5)
+    T = robot.fk_all(-np.pi + 2 * np.pi * rng.rand(1, robot.n))[:, robot.n]
+    lb, ub = eng.bounds(eng.goal_distances(T))
+    G = graph.from_pose(T[0])
+    lo, up = orc.bound_smoothing(G.edge, G.lower, G.upper)
+    assert np.max(np.abs(ub[0].cpu().numpy() - up)) <= 1e-12 * np.max(up)
+    assert np.max(np.abs(lb[0].cpu().numpy() - lo)) <= 1e-12 * np.max(up)
