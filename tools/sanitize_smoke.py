@@ -54,6 +54,18 @@ def main():
         eng.hessvec(Y0, g, g2)
         eng.proj(Y0, g)
         torch.cuda.synchronize()
+    # a graph above 128 nodes: group kernel with eight nodes per lane, bound smoothing without register tiles
+    from helpers import load_robot
+    from graphik_b200.utils.utils import table_environment
+    robot, graph = load_robot("kuka")
+    for k, (c, r) in enumerate(table_environment(n_height=12, n_width=10)):
+        graph.add_spherical_obstacle("o%d" % k, c, r)
+    _, T = goals_for(robot, 2, seed=1)
+    eng = BatchIK(graph, params=params)
+    out = eng.solve(T, check=True)
+    torch.cuda.synchronize()
+    assert int((out["iterations"] == 3).sum()) == 2
+    done.append("kuka+148 obstacles (N = %d)/generic" % graph.number_of_nodes())
     print("sanitize smoke ok:", " ".join(done))
 
 
