@@ -1,5 +1,5 @@
 #!/bin/bash
-# Commands behind the files in profiles/ (round 1e).  Each block is one `gpurun -- '<command>'` call on a B200 box;
+# Commands behind the files in profiles/ (round 1e, round 2 at the end).  Each block is one `gpurun -- '<command>'` call on a B200 box;
 # outputs land in gpurun_out/ and the summaries were copied to profiles/ by hand (see profiles/README.md).
 set -e
 mkdir -p gpurun_out
@@ -29,3 +29,28 @@ ncu --set full --clock-control none --import-source on -k regex:k_rtr_fast2 -s 1
 ncu --set full --clock-control none --import-source on -k regex:k_rtr_cta -s 1 -c 1 -o gpurun_out/cta -f \
     python tools/profile_workloads.py kuka_table:296:dense:1:40 > /dev/null
 # read back with: ncu -i gpurun_out/<name>.ncu-rep --page raw --csv | grep -E 'pipe_fp64|issue_active|dram__bytes|registers'
+
+# ---------------------------------------------------------------- round 2
+# the driver's bench command, its reference arm, and 2 GPUs under torchrun (weak scaling; configs[3] strong scaling)
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_bench.json
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_bench_ref.json
+# python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5
+# python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --robot chain20 --global-batch 65536
+
+# bound smoothing + initialisation: times, phase cycle counts (-DGIK_BI_PROFILE variant, built by --build-profile), ncu
+python tools/bi_bench.py ur10:65536 kuka:65536 chain20:65536 kuka_table:2048 > gpurun_out/r2q_bi_bench.jsonl
+python tools/bi_bench.py --build-profile && python tools/bi_bench.py ur10:4 chain20:4 kuka_table:4 --profile > gpurun_out/r2q_bi_profile.log
+ncu --set full --import-source on --clock-control none -k regex:k_bounds_init --launch-skip 2 -c 1 -o gpurun_out/r2q_bi_chain20 -f \
+    python tools/bi_bench.py chain20:65536 > /dev/null
+python tools/ncu_summary.py gpurun_out/r2q_bi_chain20.ncu-rep > profiles/r2q_k_bounds_init_chain20_b65536.txt
+
+# dense kernel: iteration rate (A/B against another build with --lib=<name>.so in graphik_b200/lib/) and ncu with source
+python tools/profile_workloads.py kuka_table:2368:dense:2:60
+ncu --set full --import-source on --clock-control none -k regex:k_rtr_cta --launch-skip 1 -c 1 -o gpurun_out/r2r_cta -f \
+    python tools/profile_workloads.py kuka_table:296:dense:1:40 > /dev/null
+# two-problems-per-warp kernel in the throughput regime
+python tools/profile_workloads.py ur10:65536:throughput:2:300
+
+# sanitizers over every kernel variant (incl. park / resume, N = 166 fallback)
+compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_smoke.py
+compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
