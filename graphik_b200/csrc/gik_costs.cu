@@ -195,6 +195,102 @@ k_costs_fast(int N, int n_goal, const uint32_t *__restrict__ fast_info, const do
     }
 }
 
+// Same operators for N <= 16 with the node-centric tables of the two-problems-per-warp solver kernel: a half-warp per
+// problem (lane = node), the slot description of a lane in registers for the whole launch, the loop over the slots fully
+// unrolled, and the NEXT pair of problems loaded into registers before the current one is evaluated.  ncu on the generic
+// kernel showed these operators bound by instruction issue (~420 warp instructions per problem: slot decode from
+// global tables, run-time loop, address arithmetic), not by HBM; this form needs ~150.
+// (launch bounds measured on UR10: cost + gradient 0.40 of the HBM peak without a register cap, 0.43 at 80 registers / six
+// CTAs per SM; Hessian-vector 0.52 without a cap, 0.43 with it)
+template <int SPL, int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 6 : 0)
+k_costs_duo(int N, int n_goal, const uint32_t *__restrict__ duo_info, const double *__restrict__ duo_target,
+            const double *__restrict__ Y, const double *__restrict__ Wd, const double *__restrict__ goal_d2,
+            int B, double *__restrict__ f, double *__restrict__ out)
+{
+    constexpr int WPB = kThreads / 32;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, node = lane & 15;
+    const bool valid = node < N;
+    const int goal_pad = (n_goal + 1) & ~1;
+    double *P = smem + (size_t)(warp * 2 + half) * (96 + goal_pad);   // [3][16] of this half's problem
+    double *V = P + 48;
+    double *goal = V + 48;
+    int nbr[SPL];
+    uint32_t kg[SPL];          // kind | goal slot + 1 << 2
+    double tstat[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) {
+        const uint32_t info = duo_info[s * 16 + node];
+        nbr[s] = GIK_SLOT_NBR(info);
+        kg[s] = GIK_SLOT_KIND(info) | (GIK_SLOT_GOAL(info) << 2);
+        tstat[s] = duo_target[s * 16 + node];
+    }
+    const int step = gridDim.x * WPB;
+    int pb = blockIdx.x * WPB + warp;                 // pair of problems 2 pb, 2 pb + 1
+    double xn[3] = {0.0, 0.0, 0.0}, wn[3] = {0.0, 0.0, 0.0};
+    auto fetch = [&](int pair) {
+        const long long b = 2LL * pair + half;
+        if (b < B && valid) {
+            const double *src = Y + ((size_t)b * N + node) * 3;
+            xn[0] = src[0]; xn[1] = src[1]; xn[2] = src[2];
+            if (MODE == 1) {
+                const double *sw = Wd + ((size_t)b * N + node) * 3;
+                wn[0] = sw[0]; wn[1] = sw[1]; wn[2] = sw[2];
+            }
+        }
+    };
+    fetch(pb);
+    for (; 2LL * pb < B; pb += step) {
+        const long long b = 2LL * pb + half;
+        const bool active = b < B;
+        const double x[3] = {xn[0], xn[1], xn[2]}, w[3] = {wn[0], wn[1], wn[2]};
+        __syncwarp();                                  // the previous pair's readers are done
+        P[node] = x[0]; P[16 + node] = x[1]; P[32 + node] = x[2];
+        if (MODE == 1) { V[node] = w[0]; V[16 + node] = w[1]; V[32 + node] = w[2]; }
+        if (active)
+            for (int k = node; k < n_goal; k += 16) goal[k] = goal_d2[(size_t)b * n_goal + k];
+        fetch(pb + step);                              // in flight while this pair is evaluated
+        __syncwarp();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};          // x, y, z of the node sum; cost share
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) {
+            const int j = nbr[s];
+            const uint32_t kind = kg[s] & 3u, gs = kg[s] >> 2;
+            const double T = gs ? goal[gs - 1] : tstat[s];
+            const double dx = x[0] - P[j], dy = x[1] - P[16 + j], dz = x[2] - P[32 + j];
+            const double d = gik_sqdist(dx, dy, dz);
+            double r = d - T;
+            const bool act = (kind == GIK_TERM_EQ) | ((kind == GIK_TERM_LO) & (r < 0.0)) |
+                             ((kind == GIK_TERM_UP) & (r > 0.0));
+            r = act ? r : 0.0;
+            if (MODE == 0) {
+                acc[3] = fma(r, r, acc[3]);
+                acc[0] = fma(r, dx, acc[0]);
+                acc[1] = fma(r, dy, acc[1]);
+                acc[2] = fma(r, dz, acc[2]);
+            } else {
+                const double wx = w[0] - V[j], wy = w[1] - V[16 + j], wz = w[2] - V[32 + j];
+                const double a2 = act ? 2.0 * (dx * wx + dy * wy + dz * wz) : 0.0;
+                acc[0] = fma(a2, dx, fma(r, wx, acc[0]));
+                acc[1] = fma(a2, dy, fma(r, wy, acc[1]));
+                acc[2] = fma(a2, dz, fma(r, wz, acc[2]));
+            }
+        }
+        if (MODE == 0 && f) {
+            double fs = 0.5 * acc[3];                  // every undirected term is seen from both ends
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) fs += __shfl_xor_sync(GIK_FULL_MASK, fs, off, 32);
+            if (node == 0 && active) f[b] = fs;
+        }
+        if (out && valid && active) {
+            double *dst = out + ((size_t)b * N + node) * 3;
+            dst[0] = 2.0 * acc[0]; dst[1] = 2.0 * acc[1]; dst[2] = 2.0 * acc[2];
+        }
+    }
+}
+
 // fixed_rank_psd_sym.py:91-113 via the 3x3 form: with X = Y^T Y and c = sum_i Z_i x Y_i,
 // (tr(X) I - X) omega = c and proj(Z)_i = Z_i - Y_i x omega.
 template <int W, int NPL>
@@ -300,10 +396,34 @@ int launch_costs_fast(const GikPlan *p, const double *Y, const double *Wd, const
     return gik_check_cuda(cudaGetLastError(), "k_costs_fast launch");
 }
 
+template <int SPL, int MODE>
+int launch_costs_duo(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
+                     double *f, double *out, cudaStream_t st)
+{
+    constexpr int WPB = kThreads / 32;
+    const int goal_pad = (p->n_goal + 1) & ~1;
+    const size_t smem = (size_t)WPB * 2 * (96 + goal_pad) * sizeof(double);
+    if (smem > 48 * 1024) return 1;
+    const int pairs = (B + 1) / 2;
+    int blocks = (pairs + WPB - 1) / WPB;
+    const int cap = p->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_costs_duo<SPL, MODE><<<blocks, kThreads, smem, st>>>(p->N, p->n_goal, p->duo_info, p->duo_target, Y, Wd, goal_d2, B, f, out);
+    return gik_check_cuda(cudaGetLastError(), "k_costs_duo launch");
+}
+
 template <int MODE>
 int dispatch_costs(const GikPlan *p, const double *Y, const double *Wd, const double *goal_d2, int B,
                    double *f, double *out, cudaStream_t st)
 {
+    if (p->duo_info) {      // N <= 16: half a warp per problem, slot tables in registers
+        int rc = 1;
+        const int d = p->maxdeg;
+        if (d <= 6) rc = launch_costs_duo<6, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        else if (d <= 9) rc = launch_costs_duo<9, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        else if (d <= 12) rc = launch_costs_duo<12, MODE>(p, Y, Wd, goal_d2, B, f, out, st);
+        if (rc <= 0) return rc;
+    }
     // 17..32 nodes: warp per problem with register-resident slot tables (KUKA: 1.4x the group kernel);
     // N <= 16 stays on the 16-lane groups, which put two problems in a warp (measured faster there)
     if (p->fast_info && p->fast_LPN == 1) {

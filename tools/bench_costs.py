@@ -10,6 +10,11 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from graphik_b200 import _lib  # noqa: E402
+for _a in sys.argv[1:]:
+    if _a.startswith("--lib="):       # an A/B variant built by hand into graphik_b200/lib/
+        _lib.LIBPATH = os.path.join(_lib.LIBDIR, _a[6:])
+        _lib.needs_build = lambda: False
 from graphik_b200.engine import BatchIK  # noqa: E402
 from graphik_b200.utils.roboturdf import load_model  # noqa: E402
 
@@ -32,7 +37,10 @@ def main():
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
+    robots = [a for a in sys.argv[1:] if not a.startswith("--")]
     for name, B in (("ur10", 1 << 21), ("kuka", 1 << 21), ("chain20", 1 << 20)):
+        if robots and name not in robots:
+            continue
         robot, graph = load_model(name)
         eng = BatchIK(graph)
         N, G = eng.plan.N, eng.plan.n_goal
