@@ -106,9 +106,9 @@ def test_batch_statistics_match_oracle(name, B):
         assert succ >= 0.9
     assert np.median(f) < 1e-13 and np.median(ref["f(x)"]) < 1e-13
     r = np.median(it) / np.median(ref["iterations"])
-    assert 0.7 < r < 1.4, r                                    # same iteration-count distribution
+    assert 0.8 < r < 1.25, r                                   # same iteration-count distribution (observed 0.98 - 1.03)
     r = n_inner.mean() / ref["n_hess"].mean()
-    assert 0.6 < r < 1.6, r
+    assert 0.7 < r < 1.4, r                                    # (a mean over a heavy tail: observed 0.99 - 1.05)
 
 
 def test_results_do_not_depend_on_batch_composition():
@@ -288,7 +288,7 @@ def test_product_pipeline_with_its_own_initialisation_vs_reference_sample(name):
     assert abs(np.mean(f < 1e-9) - np.mean(g["f"] < 1e-9)) <= tol
     assert abs(np.mean(pos < 1e-2) - np.mean(g["pose_err"] < 1e-2)) <= tol
     r = np.median(it) / np.median(g["iterations"])
-    assert 0.6 < r < 1.6, r
+    assert 0.8 < r < 1.25, r                  # observed 0.96 - 1.04
     # the joint angles returned reproduce the goal wherever the solve converged to a realisation
     T_sol, _ = eng.fk(out["q"], want_points=False)
     err = np.linalg.norm(T_sol.cpu().numpy()[:, :3, 3] - T[:, :3, 3], axis=1)
