@@ -25,11 +25,31 @@ def _torch():
     return torch
 
 
+def make_cg_opts(params=None):
+    """GikCgOpts from the reference's params dict (riemannian_solver.py:52-60)."""
+    o = _lib.CgOpts()
+    _lib.check(_lib.load().gik_cg_default_opts(ctypes.byref(o)), "gik_cg_default_opts")
+    params = params or {}
+    for key in ("mingradnorm", "minstepsize", "orth_value", "maxtime"):
+        if key in params:
+            setattr(o, key, float(params[key]))
+    if "maxiter" in params:
+        o.maxiter = int(min(float(params["maxiter"]), 2 ** 31 - 1))
+    if "beta_type" in params:      # BetaTypes value 0..3 or its name
+        bt = params["beta_type"]
+        names = ["FletcherReeves", "PolakRibiere", "HestenesStiefel", "HagerZhang"]
+        o.beta_type = names.index(bt) if isinstance(bt, str) else int(bt)
+    return o
+
+
 def make_opts(params=None):
-    """GikSolveOpts from the reference's params dict (riemannian_solver.py:41-50)."""
+    """GikSolveOpts from the reference's params dict (riemannian_solver.py:41-50); GikCgOpts when
+    params["solver"] == "ConjugateGradient"."""
+    params = params or {}
+    if params.get("solver", "TrustRegions") == "ConjugateGradient":
+        return make_cg_opts(params)
     o = _lib.SolveOpts()
     _lib.check(_lib.load().gik_default_opts(ctypes.byref(o)), "gik_default_opts")
-    params = params or {}
     for key in ("mingradnorm", "theta", "kappa", "rho_prime", "rho_regularization", "Delta_bar", "Delta0", "maxtime"):
         if key in params:
             setattr(o, key, float(params[key]))
@@ -200,6 +220,14 @@ class BatchIK:
         trace = torch.full((B, trace_rows, 6), float("nan"), dtype=torch.float64, device=self.device) \
             if trace_rows else None
         o = opts or self.opts
+        if isinstance(o, _lib.CgOpts):      # params["solver"] == "ConjugateGradient"; n_inner = cost evaluations
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.gik_cg_solve(self.plan.handle, _p(g2), _p(Y0), B, ctypes.byref(o), _p(Y), _p(f),
+                                                 _p(gn), _p(iters), _p(status), _p(n_inner), _p(trace),
+                                                 int(trace_rows), _p(self._counter()), self._stream()), "gik_cg_solve")
+            self.launches += 2
+            return {"x": Y, "f(x)": f, "gradnorm": gn, "iterations": iters, "status": status,
+                    "n_inner": n_inner, "trace": trace}
         with torch.cuda.device(self.device):
             _lib.check(self.lib.gik_rtr_solve(self.plan.handle, _p(g2), _p(Y0), B, ctypes.byref(o), _p(Y), _p(f),
                                               _p(gn), _p(iters), _p(status), _p(n_inner), _p(trace),

@@ -78,6 +78,9 @@ class IKStream:
         self.eng = engine
         self.torch = engine.torch
         self.lib = engine.lib
+        if isinstance(engine.opts, _lib.CgOpts):
+            raise _lib.GikError("IKStream drives the sliced trust-region solve; solver='ConjugateGradient' runs through "
+                                "solve_batch / solve_with_riemannian")
         N = engine.plan.N
         # tCG iterations a goal must have spent in a launch before it may park once the launch has no new goal left
         # (measured on UR10, 20 x 4096 goals, one slot: 144 k solves/s at 512, 140 k at 1024, 136 k at 2048, 119 k at 4096)

@@ -12,8 +12,8 @@ Drop-in use (the reference's README / experiments/riemannian_example.py):
 New, batched entry points: `RiemannianSolver.solve_batch(T_goals)` and
 `solve_batch_with_riemannian(graph, T_goals)`.
 
-Only `solver="TrustRegions"` exists: the reference's ConjugateGradient option lives
-entirely inside pymanopt 0.2.5 (not restatable from the reference tree).
+`solver="ConjugateGradient"` (riemannian_solver.py:52-60) runs `gik_cg_solve`: pymanopt 0.2.5's published
+ConjugateGradient + LineSearchAdaptive (third-party source outside the reference tree: parity unpinned).
 """
 import time
 
@@ -31,13 +31,12 @@ class RiemannianSolver:
         self.dim = graph.dim
         self.N = graph.number_of_nodes()
         solver_type = params.get("solver", "TrustRegions")
-        if solver_type == "ConjugateGradient":
-            raise NotImplementedError(
-                "graphik_b200 implements solver='TrustRegions' only (pymanopt's ConjugateGradient "
-                "is third-party code absent from the reference tree)")
-        if solver_type != "TrustRegions":
+        if solver_type not in ("TrustRegions", "ConjugateGradient"):
             raise ValueError("params[\"solver\"] must be one of 'ConjugateGradient', 'TrustRegions'")
-        self.opts = make_opts(params)   # mingradnorm 5e-10, maxiter 3000, theta 1, kappa 0.1 (:44-50)
+        # TrustRegions: mingradnorm 5e-10, maxiter 3000, theta 1, kappa 0.1 (:44-50); ConjugateGradient: mingradnorm 1e-9,
+        # maxiter 1e5, minstepsize 1e-10, orth_value 1e11, HagerZhang (:52-60; pymanopt 0.2.5's published algorithm
+        # restated in csrc/gik_cg.cu -- the third-party source is not in the reference tree, parity unpinned)
+        self.opts = make_opts(params)
         self._engine = None
         self._static_cache = {}
 

@@ -51,6 +51,7 @@ extern "C" {
                                     gik_check_limits when asked to; riemannian_solver.py:230-232)     */
 #define GIK_STATUS_PENDING 4     /* parked by gik_rtr_solve_sliced: final values arrive with a later launch */
 #define GIK_STATUS_MAXTIME 5     /* wall time since the problem started reached maxtime               */
+#define GIK_STATUS_MINSTEP 6     /* gik_cg_solve: the line search's step fell below minstepsize       */
 
 typedef struct GikPlan GikPlan;
 
@@ -118,6 +119,21 @@ typedef struct {
     double maxtime;             /* 1000 s (pymanopt Solver default, tested first at the end of every outer
                                    iteration, then maxiter, then mingradnorm); <= 0: no time limit */
 } GikSolveOpts;
+
+/* Options of the conjugate-gradient solve (params["solver"] = "ConjugateGradient", riemannian_solver.py:52-60:
+ * pymanopt 0.2.5's ConjugateGradient with its default LineSearchAdaptive). */
+typedef struct {
+    double mingradnorm;         /* 1e-9   */
+    int32_t maxiter;            /* 100000 (the loop stops when iter + 1 >= maxiter, as pymanopt's does) */
+    double minstepsize;         /* 1e-10  */
+    double orth_value;          /* 1e11: Powell restart when |<oldgrad, newgrad>| / <newgrad, newgrad> reaches it */
+    int32_t beta_type;          /* 0 FletcherReeves, 1 PolakRibiere, 2 HestenesStiefel, 3 HagerZhang (reference default) */
+    double maxtime;             /* 1000 s; <= 0: no limit */
+    double ls_contraction;      /* 0.5  LineSearchAdaptive(contraction_factor) */
+    double ls_suff_decr;        /* 0.5  (suff_decr) */
+    int32_t ls_maxiter;         /* 10   (maxiter: cost evaluations per search, + 1) */
+    double ls_initial_stepsize; /* 1.0  */
+} GikCgOpts;
 
 /* gik_rtr_solve implementations (identical algorithm, different mapping to the SM) */
 #define GIK_KERNEL_AUTO 0        /* N <= 16: two problems per warp for batches > 32768 and for the bulk launches of
@@ -199,6 +215,18 @@ int gik_rtr_solve(const GikPlan *plan, const double *goal_d2, const double *Y_in
                   const GikSolveOpts *opts, double *Y_out, double *f, double *gradnorm,
                   int32_t *iters, int32_t *status, int32_t *n_inner, double *trace,
                   int32_t trace_rows, int32_t *work_counter, void *stream);
+
+/* RiemannianSolver(params={"solver": "ConjugateGradient"}).solver.solve (riemannian_solver.py:52-60, 206-209):
+ * pymanopt 0.2.5 ConjugateGradient + LineSearchAdaptive restated from the published algorithm (third-party source,
+ * not in the reference tree: parity unpinned, see gik_cg.cu).  Same arguments as gik_rtr_solve; n_costevals[B]
+ * (may be NULL) = cost evaluations; trace[B][trace_rows][6] (may be NULL) per iteration: step size, cost evaluations
+ * of the line search, beta, new cost, 1 if the direction was reset to the negative gradient, new gradient norm.
+ * status: CONVERGED, MAXITER, NAN, MAXTIME or MINSTEP. */
+int gik_cg_default_opts(GikCgOpts *opts);
+int gik_cg_solve(const GikPlan *plan, const double *goal_d2, const double *Y_init, int32_t B,
+                 const GikCgOpts *opts, double *Y, double *f, double *gradnorm, int32_t *iters,
+                 int32_t *status, int32_t *n_costevals, double *trace, int32_t trace_rows,
+                 int32_t *work_counter, void *stream);
 
 /* ---- Deferred stragglers -------------------------------------------------------------------------
  * The number of tCG iterations a goal needs spans two orders of magnitude (UR10: median 5 k, 0.4 % of the

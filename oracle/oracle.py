@@ -134,6 +134,100 @@ class Problem:
                 "status": status.value, "n_hess": nh.value, "trace": trace[:min(iters, trace_rows)]}
 
 
+    # conjugate-gradient solve ------------------------------------------------
+    def solve_cg(self, Y_init, params=None, trace_rows=0):
+        """RiemannianSolver(params={"solver": "ConjugateGradient"}) (riemannian_solver.py:52-60): pymanopt 0.2.5's
+        ConjugateGradient + LineSearchAdaptive on the reference's manifold (retr(Y, U) = Y + U, transp(Y, Z, U) =
+        proj(Z, U), egrad2rgrad = identity, Frobenius inner product, no preconditioner).
+
+        PARITY UNPINNED: pymanopt is a third-party dependency that is not in the reference tree (setup.py:20 pins
+        0.2.5) and the reference holds no test or vector for this branch.  This is a restatement of the published
+        algorithm of that version (pymanopt/solvers/conjugate_gradient.py, linesearch.py = Manopt's
+        conjugategradient.m, linesearch_adaptive.m), statement by statement; it is what the CUDA kernel is
+        checked against (gik_cg.cu)."""
+        q = {"mingradnorm": 1e-9, "maxiter": 10e4, "minstepsize": 1e-10, "orth_value": 10e10, "beta_type": 3,
+             "contraction_factor": .5, "suff_decr": .5, "ls_maxiter": 10, "initial_stepsize": 1}
+        q.update(params or {})
+        inner = lambda a, b: float(np.tensordot(a, b))
+        x = _f64(Y_init).copy()
+        it, stepsize, oldalpha = 0, np.nan, None
+        cost, grad = self.cost(x), self.grad(x)
+        gradnorm = np.sqrt(inner(grad, grad))
+        gradPgrad = inner(grad, grad)
+        desc = -grad
+        trace, status, costevals = [], 1, 1
+        while True:
+            # Solver._check_stopping_criterion(time0, gradnorm=gradnorm, iter=iter + 1, stepsize=stepsize)
+            if it + 1 >= q["maxiter"]:
+                status = 1
+                break
+            if gradnorm < q["mingradnorm"]:
+                status = 0
+                break
+            if stepsize < q["minstepsize"]:
+                status = 6
+                break
+            df0 = inner(grad, desc)
+            restarted = False
+            if df0 >= 0:
+                desc = -grad
+                df0 = -gradPgrad
+                restarted = True
+            # LineSearchAdaptive.search
+            norm_d = np.sqrt(inner(desc, desc))
+            alpha = float(oldalpha) if oldalpha is not None else q["initial_stepsize"] / norm_d
+            newx = x + alpha * desc
+            newf = self.cost(newx)
+            evals = 1
+            while newf > cost + q["suff_decr"] * alpha * df0 and evals <= q["ls_maxiter"]:
+                alpha *= q["contraction_factor"]
+                newx = x + alpha * desc
+                newf = self.cost(newx)
+                evals += 1
+            if newf > cost:
+                alpha = 0
+                newx = x
+            stepsize = alpha * norm_d
+            oldalpha = alpha if evals == 2 else 2 * alpha
+            costevals += evals
+            # new cost-related quantities
+            newcost, newgrad = self.cost(newx), self.grad(newx)
+            newgradPnewgrad = inner(newgrad, newgrad)
+            newgradnorm = np.sqrt(newgradPnewgrad)
+            oldgrad = proj(newx, grad)
+            orth_grads = inner(oldgrad, newgrad) / newgradPnewgrad
+            if abs(orth_grads) >= q["orth_value"]:
+                beta = 0
+                desc = -newgrad
+            else:
+                desc = proj(newx, desc)
+                bt = q["beta_type"]
+                if bt == 0:
+                    beta = newgradPnewgrad / gradPgrad
+                elif bt == 1:
+                    beta = max(0, inner(newgrad, newgrad - oldgrad) / gradPgrad)
+                elif bt == 2:
+                    diff = newgrad - oldgrad
+                    den = inner(diff, desc)
+                    beta = 1 if den == 0 else max(0, inner(newgrad, diff) / den)
+                else:
+                    diff = newgrad - oldgrad
+                    Pdiff = newgrad - oldgrad          # Poldgrad = transp(x, newx, Pgrad) = oldgrad (no preconditioner)
+                    deno = inner(diff, desc)
+                    numo = inner(diff, newgrad)
+                    numo -= 2 * inner(diff, Pdiff) * inner(desc, newgrad) / deno
+                    beta = numo / deno
+                    eta_HZ = -1 / (np.sqrt(inner(desc, desc)) * min(0.01, newgradnorm))
+                    beta = max(beta, eta_HZ)
+                desc = -newgrad + beta * desc
+            if len(trace) < trace_rows:
+                trace.append([stepsize, evals, beta, newcost, 1.0 if restarted else 0.0, newgradnorm])
+            x, cost, grad, gradnorm, gradPgrad = newx, newcost, newgrad, newgradnorm, newgradPnewgrad
+            it += 1
+        return {"x": x, "f(x)": cost, "gradnorm": gradnorm, "iterations": it, "status": status,
+                "stepsize": stepsize, "costevals": costevals, "trace": np.array(trace).reshape(-1, 6)}
+
+
 def default_params(params=None):
     q = Params()
     lib().orc_default_params(ctypes.byref(q))

@@ -45,8 +45,8 @@ def test_riemannian_solver_solve_signature_and_log():
     assert isinstance(Y, np.ndarray) and Y.shape == (16, 3)
     with pytest.raises(Exception):
         solver.solve(D_goal, omega)                      # neither bounds nor Y_init (:199-200)
-    with pytest.raises(NotImplementedError):
-        RiemannianSolver(graph, {"solver": "ConjugateGradient"})
+    with pytest.raises(ValueError):                      # riemannian_solver.py:61-64
+        RiemannianSolver(graph, {"solver": "SteepestDescent"})
     sol3 = RiemannianSolver(graph, {"maxiter": 5}).solve(D_goal, omega, use_limits=True, Y_init=g["Y_init"][0])
     assert sol3["iterations"] == 5
 
