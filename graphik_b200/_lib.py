@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libgraphik_b200.so")
-SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_rtr_cta.cu", "gik_bounds_init.cu", "gik_joints.cu", "gik_fantope.cu", "gik_cg.cu"]
+SOURCES = ["gik_plan.cu", "gik_costs.cu", "gik_rtr.cu", "gik_rtr_fast.cu", "gik_rtr_duo.cu", "gik_rtr_cta.cu", "gik_bounds_init.cu", "gik_joints.cu", "gik_fantope.cu", "gik_cg.cu", "gik_sdp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static"]
@@ -107,13 +107,18 @@ class CgOpts(ctypes.Structure):
     ]
 
 
+class SdpOpts(ctypes.Structure):
+    _fields_ = [("tol", ctypes.c_double), ("maxiter", ctypes.c_int32), ("tau", ctypes.c_double),
+                ("x0", ctypes.c_double)]
+
+
 # every symbol include/graphik_b200.h declares
 EXPORTS = [
     "gik_last_error", "gik_version", "gik_default_opts", "gik_plan_create", "gik_plan_destroy",
     "gik_plan_info", "gik_goal_distances", "gik_cost_grad", "gik_hessvec", "gik_proj", "gik_bounds",
     "gik_init", "gik_bounds_init", "gik_rtr_solve", "gik_joints", "gik_fk", "gik_check_limits",
     "gik_carry_bytes", "gik_carry_init", "gik_rtr_solve_sliced", "gik_workspace_bytes", "gik_fantope",
-    "gik_cg_default_opts", "gik_cg_solve",
+    "gik_cg_default_opts", "gik_cg_solve", "gik_sdp_default_opts", "gik_sdp_solve",
 ]
 
 _lib = None
@@ -157,6 +162,8 @@ def load():
         "gik_rtr_solve_sliced": [vp, vp, vp, i32, ctypes.POINTER(SolveOpts), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp,
                                  vp, vp],
         "gik_fantope": [i32, i32, vp, i32, vp, vp, vp],
+        "gik_sdp_default_opts": [ctypes.POINTER(SdpOpts)],
+        "gik_sdp_solve": [i32, i32, vp, vp, vp, vp, i32, ctypes.POINTER(SdpOpts), vp, vp, vp, vp, vp, vp, vp],
         "gik_cg_default_opts": [ctypes.POINTER(CgOpts)],
         "gik_cg_solve": [vp, vp, vp, i32, ctypes.POINTER(CgOpts), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
         "gik_joints": [vp, vp, vp, i32, vp, vp],

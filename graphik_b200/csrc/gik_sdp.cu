@@ -1,0 +1,411 @@
+// gik_sdp.cu -- the semidefinite programs of CIDGIK's convex iteration, batched.
+//
+// Reference: solve_linear_cost_sdp (solvers/sdp_snl.py:874-967) hands
+//     minimise <C, Z>  s.t.  <A_k, Z> = b_k,  Z[-d:, -d:] = I,  Z >= 0
+// to MOSEK through cvxpy (sdp_snl.py:952), once per convex iteration (solvers/convex_iteration.py:221-234).  MOSEK is
+// closed third-party code that is not in the reference tree and cannot be installed here: this kernel is NOT a
+// restatement of it and PARITY WITH IT IS UNPINNED.  It solves the same programs with the same class of method
+// (infeasible-start primal-dual interior point, HKM direction, Mehrotra predictor-corrector), to the tolerances the
+// reference hands MOSEK (1e-6, solvers/sdp_formulations.py:10) or tighter, and is checked against a numpy statement
+// of the same algorithm (oracle/cidgik.py: solve_sdp) and through solver-independent optimality certificates
+// (tests/test_gpu_cidgik.py).
+//
+// Form.  Every constraint of the reference's program is a squared distance between two points, or an entry of the
+// identity block: in the coordinates the host prepares (solvers/convex_iteration.py: the face of the cone the
+// feasible set lives on) each one reads  w_k^T X w_k = b_k  with a vector w_k, so the solver takes
+//     minimise <C, X>  s.t.  w_k^T X w_k = b_k (k < M),  X >= 0          (dual: S = C - sum y_k w_k w_k^T >= 0)
+// and the Schur complement of the HKM direction is a Hadamard product,
+//     M_kl = <w_k w_k^T, X w_l w_l^T S^-1> = (w_k^T X w_l) (w_l^T S^-1 w_k).
+//
+// Mapping: one CTA of 128 threads per program, everything in shared memory (N <= 32, M <= 96; a UR10 program has
+// N = 6, M = 15).  Matrix products are spread over the CTA; the factorisations (Cholesky of S, of M and of the trial
+// points of the step-length search -- no eigenvalue problem anywhere) and the triangular solves run on warp 0 with a
+// lane per row.  HBM traffic is the problem data in and the solution out, once.
+#include "gik_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kMaxN = 32, kMaxM = 96;
+
+struct SdpArgs {
+    int N, M, B;
+    const double *C, *W, *b;
+    const int32_t *active;
+    GikSdpOpts o;
+    double *X, *y, *obj, *resid;
+    int32_t *iters, *status;
+};
+
+// sums of K per-thread values over the CTA, the same on every thread afterwards (fixed order: deterministic)
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(GIK_FULL_MASK, v[k], o, 32);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[warp * K + k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) s += scratch[w * K + k];
+        v[k] = s;
+    }
+}
+
+// Out[r x c] = A[r x n] B[n x c], row major
+__device__ __forceinline__ void matmul(double *Out, const double *A, const double *Bm, int r, int n, int c)
+{
+    for (int e = threadIdx.x; e < r * c; e += kThreads) {
+        const int i = e / c, j = e % c;
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s = fma(A[i * n + k], Bm[k * c + j], s);
+        Out[e] = s;
+    }
+}
+
+// Lower Cholesky factor of the n x n matrix A (leading dimension n) into L (may alias A) on ONE warp, lane r owning
+// the rows r, r + 32, r + 64.  False (on every lane) when a pivot is not positive and finite.
+__device__ bool warp_cholesky(const double *A, double *L, int n, int lane)
+{
+    for (int j = 0; j < n; ++j) {
+        double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int i = lane + 32 * q;
+            if (i >= j && i < n) {
+                double t = A[i * n + j];
+                for (int k = 0; k < j; ++k) t = fma(-L[i * n + k], L[j * n + k], t);
+                s[q] = t;
+            }
+        }
+        const int oq = j >> 5;
+        const double mine = oq == 0 ? s[0] : (oq == 1 ? s[1] : s[2]);
+        const double dj = __shfl_sync(GIK_FULL_MASK, mine, j & 31, 32);
+        if (!(dj > 0.0) || !isfinite(dj)) return false;
+        const double r = sqrt(dj);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int i = lane + 32 * q;
+            if (i == j) L[i * n + j] = r;
+            else if (i > j && i < n) L[i * n + j] = s[q] / r;
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// x <- (L L^T)^-1 x on one warp
+__device__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
+{
+    for (int j = 0; j < n; ++j) {
+        double p = 0.0;
+        for (int k = lane; k < j; k += 32) p = fma(L[j * n + k], x[k], p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
+        if (lane == 0) x[j] = (x[j] - p) / L[j * n + j];
+        __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        double p = 0.0;
+        for (int k = j + 1 + lane; k < n; k += 32) p = fma(L[k * n + j], x[k], p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
+        if (lane == 0) x[j] = (x[j] - p) / L[j * n + j];
+        __syncwarp();
+    }
+}
+
+// Largest alpha in {1} U (0, 1) with X + alpha dX positive definite, to within 3 %: geometric backtracking by 0.7,
+// then four bisections of the bracket (oracle/cidgik.py: _max_step).  Warp 0 only; T, L: n x n scratch.
+__device__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane)
+{
+    auto inside = [&](double alpha) {
+        for (int e = lane; e < n * n; e += 32) T[e] = fma(alpha, dX[e], X[e]);
+        __syncwarp();
+        const bool ok = warp_cholesky(T, L, n, lane);
+        __syncwarp();
+        return ok;
+    };
+    if (inside(1.0)) return 1.0;
+    double hi = 1.0, lo = 0.7;
+    while (!inside(lo)) {
+        hi = lo;
+        lo *= 0.7;
+        if (lo < 1e-12) return 0.0;
+    }
+    for (int r = 0; r < 4; ++r) {
+        const double mid = 0.5 * (lo + hi);
+        if (inside(mid)) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
+{
+    extern __shared__ double sm[];
+    const int N = a.N, M = a.M, NN = N * N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *C = sm, *X = C + NN, *S = X + NN, *Sinv = S + NN, *Rd = Sinv + NN, *dX = Rd + NN, *dS = dX + NN,
+           *corr = dS + NN, *T1 = corr + NN, *T2 = T1 + NN, *L = T2 + NN;
+    double *W = L + NN, *P = W + M * N, *Q = P + M * N, *G = Q + M * N;
+    double *bv = G + M * M, *yv = bv + M, *rp = yv + M, *dy = rp + M, *red = dy + M;   // red: [4 * 8] + flags
+    double *flag = red + 32;                                                           // [4]
+
+    for (int prob = blockIdx.x; prob < a.B; prob += gridDim.x) {
+        if (a.active && !a.active[prob]) continue;
+        __syncthreads();
+        for (int e = tid; e < NN; e += kThreads) {
+            const int i = e / N, j = e % N;
+            C[e] = a.C[(size_t)prob * NN + e];
+            X[e] = S[e] = i == j ? a.o.x0 : 0.0;
+        }
+        for (int e = tid; e < M * N; e += kThreads) W[e] = a.W[(size_t)prob * M * N + e];
+        for (int k = tid; k < M; k += kThreads) { bv[k] = a.b[(size_t)prob * M + k]; yv[k] = 0.0; }
+        __syncthreads();
+        double nb, nC;
+        {
+            double v[2] = {0.0, 0.0};
+            for (int k = tid; k < M; k += kThreads) v[0] = fma(bv[k], bv[k], v[0]);
+            for (int e = tid; e < NN; e += kThreads) v[1] = fma(C[e], C[e], v[1]);
+            block_sum<2>(v, red);
+            nb = 1.0 + sqrt(v[0]);
+            nC = 1.0 + sqrt(v[1]);
+        }
+        int status = GIK_SDP_INACCURATE, it = 0;
+        double resid = INFINITY, pobj = 0.0;
+        for (it = 0;; ++it) {
+            // residuals
+            matmul(P, W, X, M, N, N);
+            for (int e = tid; e < NN; e += kThreads) {
+                const int i = e / N, j = e % N;
+                double s = C[e] - S[e];
+                for (int k = 0; k < M; ++k) s = fma(-yv[k] * W[k * N + i], W[k * N + j], s);
+                Rd[e] = s;
+            }
+            __syncthreads();
+            for (int k = tid; k < M; k += kThreads) {
+                double s = bv[k];
+                for (int j = 0; j < N; ++j) s = fma(-P[k * N + j], W[k * N + j], s);
+                rp[k] = s;
+            }
+            __syncthreads();
+            double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int e = tid; e < NN; e += kThreads) {
+                v[0] = fma(X[e], S[e], v[0]);
+                v[1] = fma(C[e], X[e], v[1]);
+                v[2] = fma(Rd[e], Rd[e], v[2]);
+                const double t = C[e] - Rd[e];
+                v[3] = fma(t, t, v[3]);
+            }
+            for (int k = tid; k < M; k += kThreads) {
+                v[4] = fma(bv[k], yv[k], v[4]);
+                v[5] = fma(rp[k], rp[k], v[5]);
+            }
+            block_sum<6>(v, red);
+            const double mu = v[0] / N, dobj = v[4];
+            pobj = v[1];
+            const double pres = sqrt(v[5]) / nb, dres = sqrt(v[2]) / nC;
+            const double gap = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
+            if (!isfinite(pobj + dobj + pres + dres)) { status = GIK_SDP_NUMERIC; break; }
+            resid = fmax(pres, fmax(dres, gap));
+            if (resid < a.o.tol) { status = GIK_SDP_OPTIMAL; break; }
+            // dual improving ray: A^T y + S ~ 0 with b^T y > 0 certifies that the program has no feasible point
+            if (dobj > 0.0 && sqrt(v[3]) / dobj < 1e-8) { status = GIK_SDP_INFEASIBLE; break; }
+            if (it >= a.o.maxiter) break;
+
+            // S = L L^T, S^-1
+            if (warp == 0) {
+                const bool ok = warp_cholesky(S, L, N, lane);
+                if (lane == 0) flag[0] = ok ? 1.0 : 0.0;
+                if (ok && lane < N) {            // column `lane` of L^-1 into T1
+                    const int j = lane;
+                    for (int i = 0; i < j; ++i) T1[i * N + j] = 0.0;
+                    for (int i = j; i < N; ++i) {
+                        double s = i == j ? 1.0 : 0.0;
+                        for (int k = j; k < i; ++k) s = fma(-L[i * N + k], T1[k * N + j], s);
+                        T1[i * N + j] = s / L[i * N + i];
+                    }
+                }
+            }
+            __syncthreads();
+            if (flag[0] == 0.0) break;
+            for (int e = tid; e < NN; e += kThreads) {
+                const int i = e / N, j = e % N;
+                double s = 0.0;
+                for (int k = i > j ? i : j; k < N; ++k) s = fma(T1[k * N + i], T1[k * N + j], s);
+                Sinv[e] = s;
+            }
+            __syncthreads();
+            // Schur complement (lower triangle) and its factor
+            matmul(Q, W, Sinv, M, N, N);
+            __syncthreads();
+            for (int e = tid; e < M * M; e += kThreads) {
+                const int k = e / M, l = e % M;
+                if (l > k) continue;
+                double u = 0.0, w = 0.0;
+                for (int j = 0; j < N; ++j) {
+                    u = fma(P[k * N + j], W[l * N + j], u);
+                    w = fma(Q[l * N + j], W[k * N + j], w);
+                }
+                G[e] = u * w;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const bool ok = warp_cholesky(G, G, M, lane);
+                if (lane == 0) flag[0] = ok ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (flag[0] == 0.0) break;      // cond(M) ~ 1 / mu^2: rounding broke the factorisation; keep the iterate
+
+            // dX, dS, dy for the centring target nu (with the second-order term `corr` when use_corr)
+            auto direction = [&](double nu, bool use_corr) {
+                for (int e = tid; e < NN; e += kThreads) T1[e] = Rd[e] + S[e];
+                __syncthreads();
+                matmul(T2, X, T1, N, N, N);
+                __syncthreads();
+                for (int e = tid; e < NN; e += kThreads) {
+                    double t = T2[e];
+                    if (e / N == e % N) t -= nu;
+                    if (use_corr) t += corr[e];
+                    T2[e] = t;
+                }
+                __syncthreads();
+                matmul(T1, T2, Sinv, N, N, N);
+                __syncthreads();
+                for (int k = tid; k < M; k += kThreads) {
+                    double s = rp[k];
+                    for (int i = 0; i < N; ++i) {
+                        double r = 0.0;
+                        for (int j = 0; j < N; ++j) r = fma(T1[i * N + j], W[k * N + j], r);
+                        s = fma(W[k * N + i], r, s);
+                    }
+                    dy[k] = s;
+                }
+                __syncthreads();
+                if (warp == 0) warp_cholesky_solve(G, dy, M, lane);
+                __syncthreads();
+                for (int e = tid; e < NN; e += kThreads) {
+                    const int i = e / N, j = e % N;
+                    double s = Rd[e];
+                    for (int k = 0; k < M; ++k) s = fma(-dy[k] * W[k * N + i], W[k * N + j], s);
+                    dS[e] = s;
+                }
+                __syncthreads();
+                matmul(T2, X, dS, N, N, N);
+                __syncthreads();
+                if (use_corr) {
+                    for (int e = tid; e < NN; e += kThreads) T2[e] += corr[e];
+                    __syncthreads();
+                }
+                matmul(T1, T2, Sinv, N, N, N);
+                __syncthreads();
+                for (int e = tid; e < NN; e += kThreads) T2[e] = nu * Sinv[e] - X[e] - T1[e];
+                __syncthreads();
+                for (int e = tid; e < NN; e += kThreads) {
+                    const int i = e / N, j = e % N;
+                    dX[e] = 0.5 * (T2[i * N + j] + T2[j * N + i]);
+                }
+                __syncthreads();
+            };
+            auto step_lengths = [&]() {            // flag[1] = primal, flag[2] = dual
+                if (warp == 0) {
+                    const double ap = warp_max_step(X, dX, T1, L, N, lane);
+                    const double ad = warp_max_step(S, dS, T1, L, N, lane);
+                    if (lane == 0) { flag[1] = ap; flag[2] = ad; }
+                }
+                __syncthreads();
+            };
+
+            direction(0.0, false);
+            step_lengths();
+            double ap = flag[1], ad = flag[2];
+            double m[1] = {0.0};
+            for (int e = tid; e < NN; e += kThreads) m[0] = fma(fma(ap, dX[e], X[e]), fma(ad, dS[e], S[e]), m[0]);
+            block_sum<1>(m, red);
+            const double ratio = fmax(m[0] / N / mu, 0.0);
+            const double sigma = fmin(1.0, ratio * ratio * ratio);
+            matmul(corr, dX, dS, N, N, N);
+            __syncthreads();
+            direction(sigma * mu, true);
+            step_lengths();
+            ap = flag[1];
+            ad = flag[2];
+            ap = ap == 1.0 ? 1.0 : a.o.tau * ap;         // a full Newton step when it stays inside the cone
+            ad = ad == 1.0 ? 1.0 : a.o.tau * ad;
+            __syncthreads();
+            for (int e = tid; e < NN; e += kThreads) {
+                X[e] = fma(ap, dX[e], X[e]);
+                S[e] = fma(ad, dS[e], S[e]);
+            }
+            for (int k = tid; k < M; k += kThreads) yv[k] = fma(ad, dy[k], yv[k]);
+            __syncthreads();
+        }
+        __syncthreads();
+        for (int e = tid; e < NN; e += kThreads) a.X[(size_t)prob * NN + e] = X[e];
+        if (a.y) for (int k = tid; k < M; k += kThreads) a.y[(size_t)prob * M + k] = yv[k];
+        if (tid == 0) {
+            a.obj[prob] = pobj;
+            a.resid[prob] = resid;
+            a.iters[prob] = it;
+            a.status[prob] = status;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gik_sdp_default_opts(GikSdpOpts *o)
+{
+    if (!o) { gik_set_error("gik_sdp_default_opts: null argument"); return GIK_EINVAL; }
+    o->tol = 1e-8;       // aimed at; the reference asks MOSEK for 1e-6 (sdp_formulations.py:10)
+    o->maxiter = 50;
+    o->tau = 0.95;       // fraction of the step to the boundary of the cone
+    o->x0 = 10.0;        // X = S = x0 I at the start
+    return GIK_OK;
+}
+
+extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const double *b,
+                             const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
+                             double *obj, double *resid, int32_t *iters, int32_t *status, void *stream)
+{
+    if (B == 0) return GIK_OK;
+    if (B < 0 || N < 1 || M < 1 || !C || !W || !b || !X || !obj || !resid || !iters || !status) {
+        gik_set_error("gik_sdp_solve: bad argument");
+        return GIK_EINVAL;
+    }
+    if (N > kMaxN || M > kMaxM) {
+        gik_set_error("gik_sdp_solve: N = %d, M = %d exceed the limits %d, %d", N, M, kMaxN, kMaxM);
+        return GIK_ELIMIT;
+    }
+    SdpArgs a;
+    a.N = N; a.M = M; a.B = B; a.C = C; a.W = W; a.b = b; a.active = active;
+    if (opts) a.o = *opts; else gik_sdp_default_opts(&a.o);
+    if (!(a.o.tol > 0.0) || a.o.maxiter < 1 || !(a.o.tau > 0.0 && a.o.tau < 1.0) || !(a.o.x0 > 0.0)) {
+        gik_set_error("gik_sdp_solve: tol > 0, maxiter >= 1, 0 < tau < 1, x0 > 0 required");
+        return GIK_EINVAL;
+    }
+    a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = iters; a.status = status;
+    const size_t doubles = (size_t)11 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)4 * M + 32 + 4;
+    const size_t smem = doubles * sizeof(double);
+    if (smem > 227 * 1024) {
+        gik_set_error("gik_sdp_solve: needs %zu bytes of shared memory per CTA", smem);
+        return GIK_ELIMIT;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    GIK_CUDA(cudaGetDevice(&dev));
+    GIK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GIK_CUDA(cudaFuncSetAttribute(k_sdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdp, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = sms * per_sm;
+    if (blocks > B) blocks = B;
+    k_sdp<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
+    return gik_check_cuda(cudaGetLastError(), "k_sdp launch");
+}

@@ -275,11 +275,37 @@ int gik_fk(const GikPlan *plan, const double *q, int32_t B, double *T_ee, double
 int gik_check_limits(const GikPlan *plan, const double *Y, double tol, int32_t B, int32_t *n_broken,
                      int32_t *status, void *stream);
 
-/* CIDGIK, the closed-form Fantope step only: solve_fantope_closed_form (solvers/convex_iteration.py:43-53),
+/* CIDGIK, the closed-form Fantope step: solve_fantope_closed_form (solvers/convex_iteration.py:43-53),
  * C[b] = U U^T with U the eigenvectors of the n - d smallest eigenvalues of the symmetric G[b][n][n] (n <= 32);
- * eigvals[B][n] ascending (may be NULL).  The semidefinite programs of the convex iteration (MOSEK through cvxpy,
- * sdp_snl.py:874-967) are not part of this library. */
+ * eigvals[B][n] ascending (may be NULL). */
 int gik_fantope(int32_t n, int32_t d, const double *G, int32_t B, double *C, double *eigvals, void *stream);
+
+/* CIDGIK, the semidefinite programs of the convex iteration: solve_linear_cost_sdp (solvers/sdp_snl.py:874-967,
+ * cvxpy -> MOSEK at :952).  MOSEK is closed third-party code outside the reference tree: PARITY UNPINNED; this is a
+ * primal-dual interior-point method (HKM direction, Mehrotra predictor-corrector) for B programs of the form
+ *     minimise <C, X>  s.t.  w_k^T X w_k = b_k (k < M),  X >= 0 (N x N)
+ * which is the form every constraint of the reference's program takes (a squared distance between two points, an
+ * entry of the identity block) once the host has written the points in the coordinates of the face the feasible set
+ * lives on (graphik_b200/solvers/convex_iteration.py).  C[B][N][N], W[B][M][N], b[B][M]; active[B] (may be NULL):
+ * programs with active[b] == 0 are skipped and their outputs left untouched.  X[B][N][N], y[B][M] (dual, may be
+ * NULL), obj[B] = <C, X>, resid[B] = max(relative primal residual, relative dual residual, relative gap) of the
+ * returned iterate, iters[B], status[B].  N <= 32, M <= 96 (GIK_ELIMIT beyond). */
+#define GIK_SDP_OPTIMAL 0        /* resid < tol                                                             */
+#define GIK_SDP_INACCURATE 1     /* stopped by maxiter or by a numerical breakdown of the Schur complement
+                                    factorisation (cond ~ 1 / mu^2): last iterate returned, see resid      */
+#define GIK_SDP_INFEASIBLE 2     /* dual improving ray found: the program has no feasible point
+                                    (INFEASIBLE of convex_iteration.py:237-240)                             */
+#define GIK_SDP_NUMERIC 3        /* non-finite data or iterate (SOLVER_ERROR of convex_iteration.py:241-244) */
+typedef struct {
+    double tol;                 /* 1e-8 (the reference asks MOSEK for 1e-6, sdp_formulations.py:10) */
+    int32_t maxiter;            /* 50   */
+    double tau;                 /* 0.95 fraction of the step to the boundary of the cone */
+    double x0;                  /* 10   X = S = x0 I at the start */
+} GikSdpOpts;
+int gik_sdp_default_opts(GikSdpOpts *opts);
+int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const double *b,
+                  const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
+                  double *obj, double *resid, int32_t *iters, int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,145 @@
+"""CIDGIK on the GPU: gik_sdp_solve and the batched convex iteration.
+
+PARITY WITH THE REFERENCE'S SOLVER IS UNPINNED: the reference solves its semidefinite programs with MOSEK (closed
+source, not installable here) and holds no vector of a solve.  Pinned instead: (1) the program itself against the
+reference's matrices (tests/test_cidgik_cpu.py), (2) kernel == numpy statement of the same interior-point method on the
+same data, (3) solver-independent optimality certificates of the kernel's answers, (4) the end result -- the recovered
+joint angles reach the goal pose."""
+import numpy as np
+import pytest
+
+from helpers import load_robot, random_goals
+
+pytestmark = pytest.mark.gpu
+
+
+def _first_programs(name, B, seed):
+    import torch
+    from graphik_b200.solvers.convex_iteration import CidgikPlan
+    robot, graph = load_robot(name)
+    plan = CidgikPlan(graph)
+    Q, T = random_goals(robot, B, seed)
+    anchors, W, b, V = plan.assemble(T, device="cuda")
+    C = torch.matmul(V.transpose(1, 2), V).contiguous()           # C = I in the reference's coordinates
+    return robot, graph, plan, T, C, W, b, V
+
+
+@pytest.mark.parametrize("name", ["ur10", "kuka", "lwa4d"])
+def test_sdp_kernel_matches_the_numpy_statement(name):
+    from oracle import cidgik as cg
+    from graphik_b200.solvers.convex_iteration import sdp_solve_batch
+    robot, graph, plan, T, C, W, b, V = _first_programs(name, 8, 11)
+    out = sdp_solve_batch(C, W, b)
+    X, y = out["X"].cpu().numpy(), out["y"].cpu().numpy()
+    Cn, Wn, bn = C.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy()
+    for k in range(8):
+        A = np.einsum("ki,kj->kij", Wn[k], Wn[k])
+        ref = cg.solve_sdp(Cn[k], A, bn[k])
+        assert int(out["status"][k]) == ref["status"]
+        assert abs(int(out["iters"][k]) - ref["iters"]) <= 1
+        assert abs(float(out["obj"][k]) - ref["obj"]) < 1e-7 * (1 + abs(ref["obj"]))
+        if ref["status"] == cg.STATUS_OPTIMAL:
+            np.testing.assert_allclose(X[k], ref["X"], rtol=0, atol=1e-5)
+        # optimality certificate of the kernel's own answer (nothing of the oracle's iterate in it)
+        cert = cg.certificate(Cn[k], A, bn[k], X[k], y[k])
+        tol = 1e-7 if int(out["status"][k]) == 0 else 1e-4
+        assert cert["pres"] < tol and cert["gap"] < tol, cert
+        assert cert["min_eig_X"] > -1e-10 and cert["min_eig_S"] > -1e-8, cert
+        assert float(out["resid"][k]) < tol
+
+
+def test_sdp_kernel_edge_cases():
+    """Skipped programs keep their outputs; an infeasible program is reported; limits and bad arguments are errors."""
+    import torch
+    from graphik_b200 import _lib
+    from graphik_b200.solvers.convex_iteration import sdp_solve_batch, make_sdp_opts, CidgikPlan
+    robot, graph, plan, T, C, W, b, V = _first_programs("ur10", 4, 2)
+    active = torch.tensor([1, 0, 1, 0], dtype=torch.int32, device="cuda")
+    out = sdp_solve_batch(C, W, b, active=active)
+    st = out["status"].cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[1] == 3 and st[3] == 3          # untouched entries keep the initial value
+    assert float(out["X"][1].abs().max()) == 0.0
+    # a goal five metres away: no realisation exists
+    Tfar = np.eye(4)
+    Tfar[:3, 3] = [5.0, 0.0, 0.0]
+    anchors, W2, b2, V2 = plan.assemble(Tfar[None], device="cuda")
+    C2 = torch.matmul(V2.transpose(1, 2), V2).contiguous()
+    out2 = sdp_solve_batch(C2, W2, b2)
+    assert int(out2["status"][0]) == 2
+    # maxiter
+    out3 = sdp_solve_batch(C, W, b, opts=make_sdp_opts({"maxiter": 3}))
+    assert np.all(out3["status"].cpu().numpy() == 1) and np.all(out3["iters"].cpu().numpy() == 3)
+    with pytest.raises(ValueError):
+        make_sdp_opts({"nonsense": 1})
+    big = torch.zeros((1, 40, 40), dtype=torch.float64, device="cuda")
+    with pytest.raises(_lib.GikError):
+        sdp_solve_batch(big, torch.zeros((1, 10, 40), dtype=torch.float64, device="cuda"),
+                        torch.zeros((1, 10), dtype=torch.float64, device="cuda"))
+
+
+def test_convex_iteration_matches_the_numpy_statement():
+    """The batched loop against oracle.convex_iterate run in the same coordinates: same number of convex iterations,
+    same SDP optima, same end points (to the accuracy a chain of up to 10 interior-point solves leaves)."""
+    from oracle import cidgik as cg
+    from graphik_b200.solvers.convex_iteration import convex_iterate_batch
+    robot, graph = load_robot("ur10")
+    n = robot.n
+    Q, T = random_goals(robot, 4, 0)
+    out = convex_iterate_batch(graph, T)
+    plan = out["plan"]
+    Wn, bn, Vn, an = (out[k].cpu().numpy() for k in ("W", "b", "V", "anchors"))
+    vals, nit, Z = out["values"].cpu().numpy(), out["n_iters"].cpu().numpy(), out["Z"].cpu().numpy()
+    same = 0
+    for k in range(4):
+        anchors = {u: an[k, i] for i, u in enumerate(plan.anchor_names)}
+        ref = cg.convex_iterate(graph.node_ids, graph.dist, anchors, coordinates=(Wn[k], bn[k], Vn[k]))
+        m = min(2, len(ref["values"]), nit[k])
+        np.testing.assert_allclose(vals[k, :m], ref["values"][:m], rtol=1e-5, atol=1e-8)     # the first programs
+        if nit[k] == len(ref["values"]):
+            same += 1
+            assert np.abs(Z[k] - ref["Z"]).max() < 1e-3
+    assert same >= 3
+
+
+@pytest.mark.parametrize("name,floor", [("ur10", 0.9), ("kuka", 0.9), ("lwa4d", 0.9)])
+def test_cidgik_end_result_reaches_the_goal(name, floor):
+    """Solver-independent: forward kinematics of the recovered joint angles against the goal pose, 128 goals.
+    (The supplement of the CIDGIK paper reports convergence in 'typically fewer than 10 iterations'.)"""
+    from graphik_b200.solvers.convex_iteration import solve_batch_with_cidgik
+    robot, graph = load_robot(name)
+    n = robot.n
+    Q, T = random_goals(robot, 128, 21)
+    out = solve_batch_with_cidgik(graph, T, as_numpy=True)
+    assert np.all(out["feasible"] == 0)                      # every goal is reachable by construction
+    Tq = robot.fk_all(out["q"])[:, n]
+    pos = np.linalg.norm(Tq[:, :3, 3] - T[:, :3, 3], axis=1)
+    rot = np.abs(Tq[:, :3, :3] - T[:, :3, :3]).max(axis=(1, 2))
+    ok = (pos < 1e-2) & (rot < 1e-2)
+    assert ok.mean() >= floor, (ok.mean(), np.sort(pos)[-8:])
+    assert np.median(pos) < 1e-4
+    last = np.array([v[~np.isnan(v)][-1] for v in out["values"]])
+    assert np.mean(last < 1e-6) >= floor                     # excess rank driven to zero (convex_iteration.py:263)
+    assert out["n_iters"].max() <= 10 and np.median(out["n_iters"]) <= 6
+    # the distance constraints hold at the extracted points wherever the iteration ended at rank 3
+    D = np.linalg.norm(out["x"][:, :, None] - out["x"][:, None], axis=-1)
+    m = ~np.isnan(graph.dist)
+    err = np.abs(D - graph.dist[None])[:, m].max(axis=1)
+    assert np.all(err[last < 1e-6] < 1e-3)
+
+
+def test_solve_with_cidgik_reference_api():
+    """convex_iteration.py:279-319: (q_sol, solution) for a reachable goal, (None, None) for an infeasible one."""
+    from graphik_b200.solvers.convex_iteration import solve_with_cidgik
+    from graphik_b200.utils.se3 import SE3
+    robot, graph = load_robot("ur10")
+    n = robot.n
+    Q, T = random_goals(robot, 1, 4)
+    q_sol, solution = solve_with_cidgik(graph, T[0])
+    assert sorted(q_sol) == sorted("p%d" % i for i in range(1, n + 1))
+    assert sorted(solution) == sorted(graph.node_ids)
+    q = np.array([q_sol["p%d" % i] for i in range(1, n + 1)])
+    assert np.abs(robot.fk_all(q[None])[0, n] - T[0]).max() < 1e-3
+    np.testing.assert_allclose(solution["p%d" % n], T[0][:3, 3], atol=1e-12)
+    Tfar = np.eye(4)
+    Tfar[:3, 3] = [5.0, 0.0, 0.0]
+    assert solve_with_cidgik(graph, Tfar) == (None, None)
