@@ -297,12 +297,14 @@ def _plan_for(graph):
 # the convex iteration, batched
 # ------------------------------------------------------------------------------------------------------------------
 def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel_eig_sum_tol=1e-3, W_init=None,
-                         sdp_params=None, device="cuda"):
+                         sdp_params=None, sdp_accept=1e-3, device="cuda"):
     """convex_iterate_sdp_snl_graph (convex_iteration.py:160-276; ranges=True, sparse=False, closed_form=True) for
     every goal of T_goals[B,4,4] at once.  Returns a dict of CUDA tensors: Z[B,N,N] (the last SDP solution of each
     goal), C, values[B,max_iters] (SDP optimum per convex iteration, NaN beyond the last), eig_sums (sum of the N - d
     smallest eigenvalues of Z, the reference's eig_value_sum_vs_iterations), n_iters[B], feasible[B] (0 feasible,
-    1 infeasible, 2 solver error), resid[B], sdp_iters[B] (interior-point iterations, summed), anchors, plan."""
+    1 infeasible, 2 solver error), resid[B], sdp_iters[B] (interior-point iterations, summed), anchors, plan.
+    A program the solver leaves with a residual above `sdp_accept` counts as a solver error (the reference's
+    SOLVER_ERROR branch, :241-244); below it an inaccurate answer is used as cvxpy's 'optimal_inaccurate' is."""
     import torch
     if not torch.cuda.is_available():
         raise _lib.GikError("graphik_b200 needs a CUDA device (B200); there is no CPU fallback")
@@ -334,8 +336,10 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
         _sdp_launch(Cr, W, b, active, opts, sdp)
         launches += 1
         on = active.bool()
-        bad = on & (sdp["status"] >= 2)                       # convex_iteration.py:237-245
-        feasible = torch.where(bad, sdp["status"] - 1, feasible)
+        code = torch.where((sdp["status"] == 1) & (sdp["resid"] > sdp_accept), torch.full_like(sdp["status"], 3),
+                           sdp["status"])
+        bad = on & (code >= 2)                                # convex_iteration.py:237-245
+        feasible = torch.where(bad, code - 1, feasible)
         on = on & ~bad
         Znew = torch.matmul(torch.matmul(V, sdp["X"]), Vt)
         Z = torch.where(on[:, None, None], Znew, Z)

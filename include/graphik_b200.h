@@ -291,13 +291,14 @@ int gik_fantope(int32_t n, int32_t d, const double *G, int32_t B, double *C, dou
  * NULL), obj[B] = <C, X>, resid[B] = max(relative primal residual, relative dual residual, relative gap) of the
  * returned iterate, iters[B], status[B].  N <= 32, M <= 96 (GIK_ELIMIT beyond). */
 #define GIK_SDP_OPTIMAL 0        /* resid < tol                                                             */
-#define GIK_SDP_INACCURATE 1     /* stopped by maxiter or by a numerical breakdown of the Schur complement
-                                    factorisation (cond ~ 1 / mu^2): last iterate returned, see resid      */
+#define GIK_SDP_INACCURATE 1     /* stopped by maxiter, by a numerical breakdown of the Schur complement
+                                    factorisation (cond ~ 1 / mu^2) or by three iterations without progress:
+                                    the best iterate is returned, see resid                                 */
 #define GIK_SDP_INFEASIBLE 2     /* dual improving ray found: the program has no feasible point
                                     (INFEASIBLE of convex_iteration.py:237-240)                             */
 #define GIK_SDP_NUMERIC 3        /* non-finite data or iterate (SOLVER_ERROR of convex_iteration.py:241-244) */
 typedef struct {
-    double tol;                 /* 1e-8 (the reference asks MOSEK for 1e-6, sdp_formulations.py:10) */
+    double tol;                 /* 1e-7 (the reference asks MOSEK for 1e-6, sdp_formulations.py:10) */
     int32_t maxiter;            /* 50   */
     double tau;                 /* 0.95 fraction of the step to the boundary of the cone */
     double x0;                  /* 10   X = S = x0 I at the start */

@@ -186,5 +186,3 @@ def test_fantope_closed_form_vs_numpy():
         assert np.max(np.abs(C @ C - C)) <= 1e-10                  # a projector
     C1, seconds = solve_fantope_closed_form(G[1], d)               # the reference's signature
     assert np.max(np.abs(C1 - C[1])) == 0.0 and seconds >= 0.0
-    with pytest.raises(NotImplementedError):
-        solve_with_cidgik(None, None)
