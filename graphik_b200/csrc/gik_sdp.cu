@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 64;     // a UR10 program has 36-entry matrices: two warps, 8 CTAs per SM at 128 registers
 constexpr int kMaxN = 32, kMaxM = 96;
 
 struct SdpArgs {
@@ -60,7 +60,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *scratch)
 }
 
 // Out[r x c] = A[r x n] B[n x c], row major
-__device__ __forceinline__ void matmul(double *Out, const double *A, const double *Bm, int r, int n, int c)
+__device__ __noinline__ void matmul(double *Out, const double *A, const double *Bm, int r, int n, int c)
 {
     for (int e = threadIdx.x; e < r * c; e += kThreads) {
         const int i = e / c, j = e % c;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void matmul(double *Out, const double *A, const doubl
 
 // Lower Cholesky factor of the n x n matrix A (leading dimension n) into L (may alias A) on ONE warp, lane r owning
 // the rows r, r + 32, r + 64.  False (on every lane) when a pivot is not positive and finite.
-__device__ bool warp_cholesky(const double *A, double *L, int n, int lane)
+__device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, int lane)
 {
     for (int j = 0; j < n; ++j) {
         double s[3] = {0.0, 0.0, 0.0};
@@ -103,7 +103,7 @@ __device__ bool warp_cholesky(const double *A, double *L, int n, int lane)
 }
 
 // x <- (L L^T)^-1 x on one warp
-__device__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
+__device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
 {
     for (int j = 0; j < n; ++j) {
         double p = 0.0;
@@ -125,7 +125,7 @@ __device__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
 
 // Largest alpha in {1} U (0, 1) with X + alpha dX positive definite, to within 3 %: geometric backtracking by 0.7,
 // then four bisections of the bracket (the oracle's _max_step).  Warp 0 only; T, L: n x n scratch.
-__device__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane)
+__device__ __noinline__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane)
 {
     auto inside = [&](double alpha) {
         for (int e = lane; e < n * n; e += 32) T[e] = fma(alpha, dX[e], X[e]);
@@ -276,8 +276,12 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
             __syncthreads();
             if (flag[0] == 0.0) break;      // cond(M) ~ 1 / mu^2: rounding broke the factorisation; keep the iterate
 
-            // dX, dS, dy for the centring target nu (with the second-order term `corr` when use_corr)
-            auto direction = [&](double nu, bool use_corr) {
+            // predictor (nu = 0), then corrector with the centring target sigma mu and the second-order term
+            // corr = dXa dSa: one body run twice keeps the kernel's code within the instruction cache
+            double nu = 0.0, ap = 0.0, ad = 0.0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const bool use_corr = pass == 1;
                 for (int e = tid; e < NN; e += kThreads) T1[e] = Rd[e] + S[e];
                 __syncthreads();
                 matmul(T2, X, T1, N, N, N);
@@ -325,30 +329,25 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                     dX[e] = 0.5 * (T2[i * N + j] + T2[j * N + i]);
                 }
                 __syncthreads();
-            };
-            auto step_lengths = [&]() {            // flag[1] = primal, flag[2] = dual
-                if (warp == 0) {
-                    const double ap = warp_max_step(X, dX, T1, L, N, lane);
-                    const double ad = warp_max_step(S, dS, T1, L, N, lane);
-                    if (lane == 0) { flag[1] = ap; flag[2] = ad; }
+                if (warp == 0) {                       // step lengths to the boundary of the cone
+                    const double sp = warp_max_step(X, dX, T1, L, N, lane);
+                    const double sd = warp_max_step(S, dS, T1, L, N, lane);
+                    if (lane == 0) { flag[1] = sp; flag[2] = sd; }
                 }
                 __syncthreads();
-            };
-
-            direction(0.0, false);
-            step_lengths();
-            double ap = flag[1], ad = flag[2];
-            double m[1] = {0.0};
-            for (int e = tid; e < NN; e += kThreads) m[0] = fma(fma(ap, dX[e], X[e]), fma(ad, dS[e], S[e]), m[0]);
-            block_sum<1>(m, red);
-            const double ratio = fmax(m[0] / N / mu, 0.0);
-            const double sigma = fmin(1.0, ratio * ratio * ratio);
-            matmul(corr, dX, dS, N, N, N);
-            __syncthreads();
-            direction(sigma * mu, true);
-            step_lengths();
-            ap = flag[1];
-            ad = flag[2];
+                ap = flag[1];
+                ad = flag[2];
+                if (pass == 0) {
+                    double m[1] = {0.0};
+                    for (int e = tid; e < NN; e += kThreads)
+                        m[0] = fma(fma(ap, dX[e], X[e]), fma(ad, dS[e], S[e]), m[0]);
+                    block_sum<1>(m, red);
+                    const double ratio = fmax(m[0] / N / mu, 0.0);
+                    nu = fmin(1.0, ratio * ratio * ratio) * mu;
+                    matmul(corr, dX, dS, N, N, N);
+                    __syncthreads();
+                }
+            }
             ap = ap == 1.0 ? 1.0 : a.o.tau * ap;         // a full Newton step when it stays inside the cone
             ad = ad == 1.0 ? 1.0 : a.o.tau * ad;
             __syncthreads();

@@ -328,11 +328,20 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
     eig_sums = torch.full((B, max_iters), float("nan"), **f64)
     n_iters = torch.zeros(B, dtype=torch.int32, device=dev)
     sdp_iters = torch.zeros(B, dtype=torch.int32, device=dev)
-    Z = torch.zeros((B, N, N), **f64)
+    # Z = V Zr V^T has its range in span(V): with V^T V = L L^T its non-zero eigenpairs are those of the Nr x Nr matrix
+    # L^T Zr L (eigenvectors V L^-T u), so the Fantope step C = I - sum over the d largest of v v^T (:43-53) is taken
+    # there and V^T C V = L (I - sum u u^T) L^T -- the N x N matrices are only formed once, at the end
     Vt = V.transpose(1, 2).contiguous()
+    G = torch.matmul(Vt, V)
+    Lc = torch.linalg.cholesky(G)
+    Lct = Lc.transpose(1, 2)
+    Nr = plan.Nr
+    Cs = torch.eye(Nr, **f64).expand(B, Nr, Nr).contiguous()            # C = I
+    Cr = G.contiguous() if W_init is None else torch.matmul(torch.matmul(Vt, C), V).contiguous()
     launches = 0
+    sdp_iters_max = torch.zeros(max_iters, dtype=torch.int32, device=dev)   # per launch: its slowest program
+    n_active = torch.zeros(max_iters, dtype=torch.int32, device=dev)
     for it in range(max_iters):
-        Cr = torch.matmul(torch.matmul(Vt, C), V).contiguous()
         _sdp_launch(Cr, W, b, active, opts, sdp)
         launches += 1
         on = active.bool()
@@ -341,15 +350,18 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
         bad = on & (code >= 2)                                # convex_iteration.py:237-245
         feasible = torch.where(bad, code - 1, feasible)
         on = on & ~bad
-        Znew = torch.matmul(torch.matmul(V, sdp["X"]), Vt)
-        Z = torch.where(on[:, None, None], Znew, Z)
-        Cnew, ev = solve_fantope_closed_form_batch(Z, d)      # :249-251
+        Zs = torch.matmul(torch.matmul(Lct, sdp["X"]), Lc)
+        Cs_new, ev = solve_fantope_closed_form_batch(Zs, d)   # :249-251
         launches += 1
-        C = torch.where(on[:, None, None], Cnew, C)
+        Cs = torch.where(on[:, None, None], Cs_new, Cs)
+        Cr = torch.where(on[:, None, None], torch.matmul(torch.matmul(Lc, Cs_new), Lct), Cr).contiguous()
         values[:, it] = torch.where(on, sdp["obj"], values[:, it])
-        eig_sums[:, it] = torch.where(on, ev[:, :N - d].sum(dim=1), eig_sums[:, it])
+        eig_sums[:, it] = torch.where(on, ev[:, :Nr - d].sum(dim=1), eig_sums[:, it])   # the other N - Nr are zero
         n_iters += on.int()
-        sdp_iters += torch.where(active.bool(), sdp["iters"], torch.zeros_like(sdp["iters"]))
+        spent = torch.where(active.bool(), sdp["iters"], torch.zeros_like(sdp["iters"]))
+        sdp_iters += spent
+        sdp_iters_max[it] = spent.max()
+        n_active[it] = active.sum()
         change = last_cost - sdp["obj"]                       # :262-266
         done = (change.abs() <= abs_eig_sum_tol) | (sdp["obj"] <= abs_eig_sum_tol) | \
                (change.abs() / last_cost.abs() < rel_eig_sum_tol)
@@ -357,9 +369,14 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
         active = (on & ~done).int()
         if int(active.sum()) == 0:
             break
+    Z = torch.matmul(torch.matmul(V, sdp["X"]), Vt)           # the last program solved for each goal
+    if W_init is None or it > 0:
+        Qb = torch.linalg.solve_triangular(Lc, Vt, upper=False).transpose(1, 2)      # V L^-T, orthonormal columns
+        eye = torch.eye(N, **f64)
+        C = eye - torch.matmul(torch.matmul(Qb, torch.eye(Nr, **f64) - Cs), Qb.transpose(1, 2))
     return {"Z": Z, "C": C, "values": values, "eig_sums": eig_sums, "n_iters": n_iters, "feasible": feasible,
             "resid": sdp["resid"], "sdp_iters": sdp_iters, "anchors": anchors, "plan": plan, "launches": launches,
-            "y": sdp["y"], "V": V, "W": W, "b": b}
+            "y": sdp["y"], "V": V, "W": W, "b": b, "sdp_iters_max": sdp_iters_max, "n_active": n_active}
 
 
 def solve_batch_with_cidgik(graph, T_goals, as_numpy=False, **kw):
@@ -384,7 +401,7 @@ def solve_batch_with_cidgik(graph, T_goals, as_numpy=False, **kw):
     q = RiemannianSolver(graph).engine.joints(Y.contiguous(), T)   # graph.joint_variables(G_sol, {p_n: T_goal}) (:317)
     res = {"q": q, "x": Y, "feasible": out["feasible"], "n_iters": out["n_iters"], "values": out["values"],
            "eig_sums": out["eig_sums"], "resid": out["resid"], "sdp_iters": out["sdp_iters"], "Z": Z,
-           "launches": out["launches"] + 1}
+           "launches": out["launches"] + 1, "sdp_iters_max": out["sdp_iters_max"], "n_active": out["n_active"]}
     if as_numpy:
         res = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
     return res
