@@ -552,7 +552,59 @@ def measure_configs(args, dev):
                     "clocks": clocks})
         del solver, eng, Ts, res, tickets, st
         torch.cuda.empty_cache()
+    out.append(measure_cidgik(dev))
     return out
+
+
+def measure_cidgik(dev, B=1024, K=8):
+    """BASELINE configs[4]: CIDGIK (solve_with_cidgik, convex_iteration.py:279-319) on UR10, 1024 goals per batch,
+    `ranges=True` as the reference calls it -- which yields no inequality for any graph the reference can build
+    (sdp_snl.py:383-385 looks at obstacle pairs only and obstacles are anchors).  The SDP solver is
+    this repo's interior-point kernel, not MOSEK: parity unpinned; `pose_reached_frac` is the
+    solver-independent check.  `cpu_port` times the numpy statement of the same algorithm on one host core."""
+    import torch
+    from graphik_b200.solvers.convex_iteration import solve_batch_with_cidgik
+    robot, graph = load_workload("ur10")
+    n = robot.n
+    Tn = [goals_for(robot, B, seed=7000 + s)[1] for s in range(K)]
+    Ts = [torch.as_tensor(T, device=dev) for T in Tn]
+    solve_batch_with_cidgik(graph, Ts[0])
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index).start()
+    # this path is ~170 short launches per batch: let nvidia-smi finish starting up (it holds driver locks that delay
+    # launches while it initialises) before the timed region begins
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+        time.sleep(0.01)
+    t0 = time.perf_counter()
+    res = [solve_batch_with_cidgik(graph, T) for T in Ts]
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ok, iters, launches = [], [], 0
+    for T, r in zip(Tn, res):
+        Tq = robot.fk_all(r["q"].cpu().numpy())[:, n]
+        ok.append((np.linalg.norm(Tq[:, :3, 3] - T[:, :3, 3], axis=1) < 1e-2) &
+                  (np.abs(Tq[:, :3, :3] - T[:, :3, :3]).max(axis=(1, 2)) < 1e-2))
+        iters.append(r["n_iters"].cpu().numpy())
+        launches += int(r["launches"])
+    # CPU: the numpy statement of the same algorithm (oracle/cidgik.py), 4 goals, one core
+    from oracle import cidgik as cg
+    from graphik_b200.solvers.convex_iteration import CidgikPlan
+    plan = CidgikPlan(graph)
+    an, W, b, V = [t.numpy() for t in plan.assemble(Tn[0][:4], device="cpu")]
+    t0 = time.perf_counter()
+    for k in range(4):
+        cg.convex_iterate(graph.node_ids, graph.dist, {u: an[k, i] for i, u in enumerate(plan.anchor_names)},
+                          coordinates=(W[k], b[k], V[k]))
+    cpu = 4 / (time.perf_counter() - t0)
+    return {"workload": "BASELINE configs[4]: CIDGIK (SDP relaxation + convex iteration), UR10, 1024 goals per batch, "
+                        "ranges=True (no inequality arises, SURVEY App. C.1); own interior-point SDP kernel, parity "
+                        "with MOSEK unpinned", "robot": "ur10", "batch": B, "steps": K, "value": B * K / dt,
+            "unit": UNIT, "seconds": dt, "pose_reached_frac": float(np.mean(ok)),
+            "convex_iterations_mean": float(np.mean(iters)), "gpu_launches": launches,
+            "cpu_port": {"value": cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "4 goals, numpy statement of the same algorithm"}, "clocks": clocks}
 
 
 def cpu_baselines(args, robot, graph, n_warm):

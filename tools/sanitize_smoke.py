@@ -6,7 +6,8 @@
 
 Every trust-region kernel variant (k_rtr_fast throughput / latency, k_rtr_duo, k_rtr_fast2, k_rtr_cta, k_rtr), the
 sliced solve with parking and resuming, k_bounds_init at N = 16 / 44 / 118 (shared memory only / with workspace),
-the streaming cost kernels, goal distances, joints, FK and the limit check -- on a handful of goals with the
+the streaming cost kernels, goal distances, joints, FK, the limit check, the conjugate-gradient solve and the CIDGIK
+kernels (SDP interior point, Fantope step) -- on a handful of goals with the
 iteration counts cut down (a sanitizer slows a kernel by two orders of magnitude).
 """
 import ctypes
@@ -66,6 +67,25 @@ def main():
     torch.cuda.synchronize()
     assert int((out["iterations"] == 3).sum()) == 2
     done.append("kuka+148 obstacles (N = %d)/generic" % graph.number_of_nodes())
+    # conjugate-gradient solve (k_cg) and CIDGIK (k_sdp with a skipped program, k_fantope), cut down
+    from graphik_b200.engine import make_opts
+    from graphik_b200.solvers.convex_iteration import convex_iterate_batch
+    for name in ("ur10", "chain20"):
+        robot, graph = load_workload(name)
+        _, T = goals_for(robot, 3, seed=2)
+        eng = BatchIK(graph)
+        g2 = eng.goal_distances(T)
+        out = eng.solve_points(g2, eng.initialization(g2), opts=make_opts({"solver": "ConjugateGradient", "maxiter": 6}))
+        torch.cuda.synchronize()
+        assert int((out["iterations"] == 5).sum()) == 3
+        done.append("%s/cg" % name)
+    for name in ("ur10", "kuka"):
+        robot, graph = load_workload(name)
+        _, T = goals_for(robot, 3, seed=2)
+        out = convex_iterate_batch(graph, T, max_iters=2, sdp_params={"maxiter": 4}, sdp_accept=float("inf"))
+        torch.cuda.synchronize()
+        assert int(out["n_iters"].max()) == 2
+        done.append("%s/cidgik" % name)
     print("sanitize smoke ok:", " ".join(done))
 
 
