@@ -71,28 +71,31 @@ __device__ __noinline__ void matmul(double *Out, const double *A, const double *
 }
 
 // Lower Cholesky factor of the n x n matrix A (leading dimension n) into L (may alias A) on ONE warp, lane r owning
-// the rows r, r + 32, r + 64.  False (on every lane) when a pivot is not positive and finite.
+// the rows r, r + 32, ... (R of them: n <= 32 R).  False (on every lane) when a pivot is not positive and finite.
+template <int R>
 __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, int lane)
 {
     for (int j = 0; j < n; ++j) {
-        double s[3] = {0.0, 0.0, 0.0};
+        double s[R];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < R; ++q) {
             const int i = lane + 32 * q;
+            s[q] = 0.0;
             if (i >= j && i < n) {
                 double t = A[i * n + j];
                 for (int k = 0; k < j; ++k) t = fma(-L[i * n + k], L[j * n + k], t);
                 s[q] = t;
             }
         }
-        const int oq = j >> 5;
-        const double mine = oq == 0 ? s[0] : (oq == 1 ? s[1] : s[2]);
+        double mine = s[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) mine = (j >> 5) == q ? s[q] : mine;
         const double dj = __shfl_sync(GIK_FULL_MASK, mine, j & 31, 32);
         if (!(dj > 0.0) || !isfinite(dj)) return false;
         const double r = sqrt(dj);
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < R; ++q) {
             const int i = lane + 32 * q;
             if (i == j) L[i * n + j] = r;
             else if (i > j && i < n) L[i * n + j] = s[q] / r;
@@ -123,14 +126,16 @@ __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int
     }
 }
 
-// Largest alpha in {1} U (0, 1) with X + alpha dX positive definite, to within 3 %: geometric backtracking by 0.7,
-// then four bisections of the bracket (the oracle's _max_step).  Warp 0 only; T, L: n x n scratch.
-__device__ __noinline__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane)
+// Largest alpha in {1} U (0, 1) with X + alpha dX positive definite: geometric backtracking by 0.7, then `bisections`
+// halvings of the bracket (four: within 3 %; the predictor only feeds the centring heuristic and takes none) -- the
+// oracle's _max_step.  Warp 0 only; T, L: n x n scratch.
+__device__ __noinline__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane,
+                                             int bisections)
 {
     auto inside = [&](double alpha) {
         for (int e = lane; e < n * n; e += 32) T[e] = fma(alpha, dX[e], X[e]);
         __syncwarp();
-        const bool ok = warp_cholesky(T, L, n, lane);
+        const bool ok = warp_cholesky<1>(T, L, n, lane);
         __syncwarp();
         return ok;
     };
@@ -141,7 +146,7 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
         lo *= 0.7;
         if (lo < 1e-12) return 0.0;
     }
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < bisections; ++r) {
         const double mid = 0.5 * (lo + hi);
         if (inside(mid)) lo = mid; else hi = mid;
     }
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
 
             // S = L L^T, S^-1
             if (warp == 0) {
-                const bool ok = warp_cholesky(S, L, N, lane);
+                const bool ok = warp_cholesky<1>(S, L, N, lane);
                 if (lane == 0) flag[0] = ok ? 1.0 : 0.0;
                 if (ok && lane < N) {            // column `lane` of L^-1 into T1
                     const int j = lane;
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
             }
             __syncthreads();
             if (warp == 0) {
-                const bool ok = warp_cholesky(G, G, M, lane);
+                const bool ok = M <= 32 ? warp_cholesky<1>(G, G, M, lane) : warp_cholesky<3>(G, G, M, lane);
                 if (lane == 0) flag[0] = ok ? 1.0 : 0.0;
             }
             __syncthreads();
@@ -330,8 +335,8 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                 }
                 __syncthreads();
                 if (warp == 0) {                       // step lengths to the boundary of the cone
-                    const double sp = warp_max_step(X, dX, T1, L, N, lane);
-                    const double sd = warp_max_step(S, dS, T1, L, N, lane);
+                    const double sp = warp_max_step(X, dX, T1, L, N, lane, pass ? 4 : 0);
+                    const double sd = warp_max_step(S, dS, T1, L, N, lane, pass ? 4 : 0);
                     if (lane == 0) { flag[1] = sp; flag[2] = sd; }
                 }
                 __syncthreads();
