@@ -552,42 +552,70 @@ def measure_configs(args, dev):
                     "clocks": clocks})
         del solver, eng, Ts, res, tickets, st
         torch.cuda.empty_cache()
-    out.append(measure_cidgik(dev))
+    out.extend(measure_cidgik(dev))
     return out
 
 
 def measure_cidgik(dev, B=1024, K=8):
     """BASELINE configs[4]: CIDGIK (solve_with_cidgik, convex_iteration.py:279-319) on UR10, 1024 goals per batch,
-    `ranges=True` as the reference calls it -- which yields no inequality for any graph the reference can build
-    (sdp_snl.py:383-385 looks at obstacle pairs only and obstacles are anchors).  The SDP solver is
-    this repo's interior-point kernel, not MOSEK: parity unpinned; `pose_reached_frac` is the
-    solver-independent check.  `cpu_port` times the numpy statement of the same algorithm on one host core."""
+    `ranges=True` as the reference calls it.  Two entries: (1) the graph as the reference builds it, for which
+    `ranges=True` yields no inequality (sdp_snl.py:383-385 looks at obstacle pairs only and the reference's obstacles are
+    anchors without robot edges); (2) obstacle_semantics="intended" with one sphere in the workspace:
+    every free joint point carries a lower-bound inequality.  The SDP solver is this repo's interior-point kernel, not
+    MOSEK: parity unpinned; `pose_reached_frac` / `clear_of_obstacle_frac` are the solver-independent
+    checks.  `cpu_port` times the numpy statement of the same algorithm on one host core."""
     import torch
     from graphik_b200.solvers.convex_iteration import solve_batch_with_cidgik
+    from graphik_b200.utils.roboturdf import load_model
+    entries = []
+    centre, radius = np.array([0.3, 0.3, 0.2]), 0.3
+    for with_sphere in (False, True):
+        if with_sphere:
+            robot, graph = load_model("ur10", graph_params={"obstacle_semantics": "intended"})
+            graph.add_spherical_obstacle("o0", centre, radius)
+        else:
+            robot, graph = load_workload("ur10")
+        n = robot.n
+        Tn = [goals_for(robot, B, seed=7000 + s)[1] for s in range(K)]
+        Ts = [torch.as_tensor(T, device=dev) for T in Tn]
+        solve_batch_with_cidgik(graph, Ts[0])
+        torch.cuda.synchronize(dev)
+        sampler = ClockSampler(dev.index).start()
+        # this path is ~170 short launches per batch: let nvidia-smi finish starting up (it holds driver locks that
+        # delay launches while it initialises) before the timed region begins
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.01)
+        t0 = time.perf_counter()
+        res = [solve_batch_with_cidgik(graph, T) for T in Ts]
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        ok, iters, launches, feas, clear = [], [], 0, [], []
+        pid = [graph.idx("p%d" % i) for i in range(1, n)]
+        for T, r in zip(Tn, res):
+            Tq = robot.fk_all(r["q"].cpu().numpy())[:, n]
+            ok.append((np.linalg.norm(Tq[:, :3, 3] - T[:, :3, 3], axis=1) < 1e-2) &
+                      (np.abs(Tq[:, :3, :3] - T[:, :3, :3]).max(axis=(1, 2)) < 1e-2))
+            iters.append(r["n_iters"].cpu().numpy())
+            feas.append(r["feasible"].cpu().numpy())
+            clear.append(np.linalg.norm(r["x"].cpu().numpy()[:, pid] - centre, axis=-1).min(axis=1) > radius - 1e-3)
+            launches += int(r["launches"])
+        ok, feas, clear = np.concatenate(ok), np.concatenate(feas), np.concatenate(clear)
+        e = {"workload": "BASELINE configs[4]: CIDGIK (SDP relaxation + convex iteration), UR10, 1024 goals per batch, "
+                         "ranges=True; own interior-point SDP kernel, parity with MOSEK unpinned; " +
+                         ("obstacle_semantics=intended, one sphere r = 0.3 m: 5 lower-bound inequalities per program"
+                          if with_sphere else "graph as the reference builds it: no inequality arises (SURVEY App. C.1)"),
+             "robot": "ur10", "batch": B, "steps": K, "value": B * K / dt, "unit": UNIT, "seconds": dt,
+             "feasible_frac": float(np.mean(feas == 0)),
+             "pose_reached_frac": float(np.mean(ok[feas == 0])),
+             "convex_iterations_mean": float(np.mean(np.concatenate(iters))), "gpu_launches": launches,
+             "clocks": clocks}
+        if with_sphere:
+            e["clear_of_obstacle_frac_where_pose_reached"] = float(np.mean(clear[(feas == 0) & ok]))
+        entries.append(e)
     robot, graph = load_workload("ur10")
-    n = robot.n
-    Tn = [goals_for(robot, B, seed=7000 + s)[1] for s in range(K)]
-    Ts = [torch.as_tensor(T, device=dev) for T in Tn]
-    solve_batch_with_cidgik(graph, Ts[0])
-    torch.cuda.synchronize(dev)
-    sampler = ClockSampler(dev.index).start()
-    # this path is ~170 short launches per batch: let nvidia-smi finish starting up (it holds driver locks that delay
-    # launches while it initialises) before the timed region begins
-    t_wait = time.perf_counter()
-    while not sampler.rows and time.perf_counter() - t_wait < 3.0:
-        time.sleep(0.01)
-    t0 = time.perf_counter()
-    res = [solve_batch_with_cidgik(graph, T) for T in Ts]
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    clocks = sampler.stop()
-    ok, iters, launches = [], [], 0
-    for T, r in zip(Tn, res):
-        Tq = robot.fk_all(r["q"].cpu().numpy())[:, n]
-        ok.append((np.linalg.norm(Tq[:, :3, 3] - T[:, :3, 3], axis=1) < 1e-2) &
-                  (np.abs(Tq[:, :3, :3] - T[:, :3, :3]).max(axis=(1, 2)) < 1e-2))
-        iters.append(r["n_iters"].cpu().numpy())
-        launches += int(r["launches"])
+    Tn = [goals_for(robot, B, seed=7000)[1]]
     # CPU: the numpy statement of the same algorithm (oracle/cidgik.py), 4 goals, one core
     from oracle import cidgik as cg
     from graphik_b200.solvers.convex_iteration import CidgikPlan
@@ -598,13 +626,9 @@ def measure_cidgik(dev, B=1024, K=8):
         cg.convex_iterate(graph.node_ids, graph.dist, {u: an[k, i] for i, u in enumerate(plan.anchor_names)},
                           coordinates=(W[k], b[k], V[k]))
     cpu = 4 / (time.perf_counter() - t0)
-    return {"workload": "BASELINE configs[4]: CIDGIK (SDP relaxation + convex iteration), UR10, 1024 goals per batch, "
-                        "ranges=True (no inequality arises, SURVEY App. C.1); own interior-point SDP kernel, parity "
-                        "with MOSEK unpinned", "robot": "ur10", "batch": B, "steps": K, "value": B * K / dt,
-            "unit": UNIT, "seconds": dt, "pose_reached_frac": float(np.mean(ok)),
-            "convex_iterations_mean": float(np.mean(iters)), "gpu_launches": launches,
-            "cpu_port": {"value": cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "4 goals, numpy statement of the same algorithm"}, "clocks": clocks}
+    entries[0]["cpu_port"] = {"value": cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                              "sample": "4 goals, numpy statement of the same algorithm"}
+    return entries
 
 
 def cpu_baselines(args, robot, graph, n_warm):

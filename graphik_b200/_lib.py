@@ -163,7 +163,7 @@ def load():
                                  vp, vp],
         "gik_fantope": [i32, i32, vp, i32, vp, vp, vp],
         "gik_sdp_default_opts": [ctypes.POINTER(SdpOpts)],
-        "gik_sdp_solve": [i32, i32, vp, vp, vp, vp, i32, ctypes.POINTER(SdpOpts), vp, vp, vp, vp, vp, vp, vp],
+        "gik_sdp_solve": [i32, i32, vp, vp, vp, vp, vp, i32, ctypes.POINTER(SdpOpts), vp, vp, vp, vp, vp, vp, vp],
         "gik_cg_default_opts": [ctypes.POINTER(CgOpts)],
         "gik_cg_solve": [vp, vp, vp, i32, ctypes.POINTER(CgOpts), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
         "gik_joints": [vp, vp, vp, i32, vp, vp],

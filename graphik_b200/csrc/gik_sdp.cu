@@ -30,7 +30,7 @@ constexpr int kMaxN = 32, kMaxM = 96;
 
 struct SdpArgs {
     int N, M, B;
-    const double *C, *W, *b;
+    const double *C, *W, *b, *tau;
     const int32_t *active;
     GikSdpOpts o;
     double *X, *y, *obj, *resid;
@@ -127,8 +127,8 @@ __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int
 }
 
 // Largest alpha in {1} U (0, 1) with X + alpha dX positive definite: geometric backtracking by 0.7, then `bisections`
-// halvings of the bracket (four: within 3 %; the predictor only feeds the centring heuristic and takes none) -- the
-// oracle's _max_step.  Warp 0 only; T, L: n x n scratch.
+// halvings of the bracket (four: within 3 %; the predictor only feeds the centring heuristic and takes none), as
+// _max_step of the oracle does.  Warp 0 only; T, L: n x n scratch.
 __device__ __noinline__ double warp_max_step(const double *X, const double *dX, double *T, double *L, int n, int lane,
                                              int bisections)
 {
@@ -153,14 +153,17 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
     return lo;
 }
 
-__global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
+// LP: the program has inequality rows (slack blocks); the equality-only instantiation carries none of that code
+template <bool LP>
+__global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
 {
     extern __shared__ double sm[];
     const int N = a.N, M = a.M, NN = N * N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *C = sm, *X = C + NN, *S = X + NN, *Sinv = S + NN, *Rd = Sinv + NN, *dX = Rd + NN, *dS = dX + NN,
            *corr = dS + NN, *T1 = corr + NN, *T2 = T1 + NN, *L = T2 + NN, *Xbest = L + NN;
     double *W = Xbest + NN, *P = W + M * N, *Q = P + M * N, *G = Q + M * N;
-    double *bv = G + M * M, *yv = bv + M, *rp = yv + M, *dy = rp + M, *ybest = dy + M, *red = ybest + M;   // red: [4 * 8]
+    double *bv = G + M * M, *yv = bv + M, *rp = yv + M, *dy = rp + M, *ybest = dy + M, *tau = ybest + M,
+           *sv = tau + M, *zv = sv + M, *dsv = zv + M, *dzv = dsv + M, *clp = dzv + M, *red = clp + M;   // red: [2 * 8]
     double *flag = red + 32;                                                           // [4]
 
     for (int prob = blockIdx.x; prob < a.B; prob += gridDim.x) {
@@ -172,8 +175,18 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
             X[e] = S[e] = i == j ? a.o.x0 : 0.0;
         }
         for (int e = tid; e < M * N; e += kThreads) W[e] = a.W[(size_t)prob * M * N + e];
-        for (int k = tid; k < M; k += kThreads) { bv[k] = a.b[(size_t)prob * M + k]; yv[k] = 0.0; }
+        for (int k = tid; k < M; k += kThreads) {
+            bv[k] = a.b[(size_t)prob * M + k];
+            yv[k] = 0.0;
+            // inequality k: w_k^T X w_k + tau_k s_k = b_k with a slack s_k >= 0 (tau = +1 upper, -1 lower bound) and its
+            // dual z_k = -tau_k y_k >= 0 -- a 1 x 1 block of the cone next to X
+            tau[k] = LP ? a.tau[k] : 0.0;
+            sv[k] = zv[k] = (LP && tau[k] != 0.0) ? a.o.x0 : 0.0;
+            dsv[k] = dzv[k] = clp[k] = 0.0;
+        }
         __syncthreads();
+        int n_ineq = 0;
+        for (int k = 0; LP && k < M; ++k) n_ineq += tau[k] != 0.0;
         double nb, nC;
         {
             double v[2] = {0.0, 0.0};
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
             }
             __syncthreads();
             for (int k = tid; k < M; k += kThreads) {
-                double s = bv[k];
+                double s = LP ? bv[k] - tau[k] * sv[k] : bv[k];
                 for (int j = 0; j < N; ++j) s = fma(-P[k * N + j], W[k * N + j], s);
                 rp[k] = s;
             }
@@ -213,9 +226,15 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
             for (int k = tid; k < M; k += kThreads) {
                 v[4] = fma(bv[k], yv[k], v[4]);
                 v[5] = fma(rp[k], rp[k], v[5]);
+                if ((LP && tau[k] != 0.0)) {
+                    const double rz = -tau[k] * yv[k] - zv[k];        // dual residual of the slack
+                    v[0] = fma(sv[k], zv[k], v[0]);
+                    v[2] = fma(rz, rz, v[2]);
+                    v[3] = fma(rz, rz, v[3]);
+                }
             }
             block_sum<6>(v, red);
-            const double mu = v[0] / N, dobj = v[4];
+            const double mu = v[0] / (N + n_ineq), dobj = v[4];
             pobj = v[1];
             const double pres = sqrt(v[5]) / nb, dres = sqrt(v[2]) / nC;
             const double gap = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
@@ -271,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                     u = fma(P[k * N + j], W[l * N + j], u);
                     w = fma(Q[l * N + j], W[k * N + j], w);
                 }
-                G[e] = u * w;
+                G[e] = u * w + (k == l && (LP && tau[k] != 0.0) ? sv[k] / zv[k] : 0.0);
             }
             __syncthreads();
             if (warp == 0) {
@@ -307,11 +326,20 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                         for (int j = 0; j < N; ++j) r = fma(T1[i * N + j], W[k * N + j], r);
                         s = fma(W[k * N + i], r, s);
                     }
+                    if ((LP && tau[k] != 0.0)) {
+                        const double rz = -tau[k] * yv[k] - zv[k];
+                        s -= tau[k] * (((nu - clp[k]) / zv[k] - sv[k]) - sv[k] / zv[k] * rz);
+                    }
                     dy[k] = s;
                 }
                 __syncthreads();
                 if (warp == 0) warp_cholesky_solve(G, dy, M, lane);
                 __syncthreads();
+                for (int k = tid; LP && k < M; k += kThreads)
+                    if ((LP && tau[k] != 0.0)) {
+                        dzv[k] = -tau[k] * yv[k] - zv[k] - tau[k] * dy[k];
+                        dsv[k] = ((nu - clp[k]) / zv[k] - sv[k]) - sv[k] / zv[k] * dzv[k];
+                    }
                 for (int e = tid; e < NN; e += kThreads) {
                     const int i = e / N, j = e % N;
                     double s = Rd[e];
@@ -342,14 +370,22 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                 __syncthreads();
                 ap = flag[1];
                 ad = flag[2];
+                for (int k = 0; LP && k < M; ++k)    // ratio test on the slacks (the same on every thread)
+                    if ((LP && tau[k] != 0.0)) {
+                        if (dsv[k] < 0.0) ap = fmin(ap, -sv[k] / dsv[k]);
+                        if (dzv[k] < 0.0) ad = fmin(ad, -zv[k] / dzv[k]);
+                    }
                 if (pass == 0) {
                     double m[1] = {0.0};
                     for (int e = tid; e < NN; e += kThreads)
                         m[0] = fma(fma(ap, dX[e], X[e]), fma(ad, dS[e], S[e]), m[0]);
+                    for (int k = tid; LP && k < M; k += kThreads)
+                        if ((LP && tau[k] != 0.0)) m[0] = fma(fma(ap, dsv[k], sv[k]), fma(ad, dzv[k], zv[k]), m[0]);
                     block_sum<1>(m, red);
-                    const double ratio = fmax(m[0] / N / mu, 0.0);
+                    const double ratio = fmax(m[0] / (N + n_ineq) / mu, 0.0);
                     nu = fmin(1.0, ratio * ratio * ratio) * mu;
                     matmul(corr, dX, dS, N, N, N);
+                    for (int k = tid; LP && k < M; k += kThreads) clp[k] = dsv[k] * dzv[k];
                     __syncthreads();
                 }
             }
@@ -360,7 +396,14 @@ __global__ void __launch_bounds__(kThreads) k_sdp(const SdpArgs a)
                 X[e] = fma(ap, dX[e], X[e]);
                 S[e] = fma(ad, dS[e], S[e]);
             }
-            for (int k = tid; k < M; k += kThreads) yv[k] = fma(ad, dy[k], yv[k]);
+            for (int k = tid; k < M; k += kThreads) {
+                yv[k] = fma(ad, dy[k], yv[k]);
+                if (LP) {
+                    sv[k] = fma(ap, dsv[k], sv[k]);
+                    zv[k] = fma(ad, dzv[k], zv[k]);
+                    clp[k] = 0.0;
+                }
+            }
             __syncthreads();
         }
         __syncthreads();
@@ -389,7 +432,7 @@ extern "C" int gik_sdp_default_opts(GikSdpOpts *o)
 }
 
 extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const double *b,
-                             const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
+                             const double *tau, const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
                              double *obj, double *resid, int32_t *iters, int32_t *status, void *stream)
 {
     if (B == 0) return GIK_OK;
@@ -402,14 +445,14 @@ extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double
         return GIK_ELIMIT;
     }
     SdpArgs a;
-    a.N = N; a.M = M; a.B = B; a.C = C; a.W = W; a.b = b; a.active = active;
+    a.N = N; a.M = M; a.B = B; a.C = C; a.W = W; a.b = b; a.tau = tau; a.active = active;
     if (opts) a.o = *opts; else gik_sdp_default_opts(&a.o);
     if (!(a.o.tol > 0.0) || a.o.maxiter < 1 || !(a.o.tau > 0.0 && a.o.tau < 1.0) || !(a.o.x0 > 0.0)) {
         gik_set_error("gik_sdp_solve: tol > 0, maxiter >= 1, 0 < tau < 1, x0 > 0 required");
         return GIK_EINVAL;
     }
     a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = iters; a.status = status;
-    const size_t doubles = (size_t)12 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)5 * M + 32 + 4;
+    const size_t doubles = (size_t)12 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)11 * M + 32 + 4;
     const size_t smem = doubles * sizeof(double);
     if (smem > 227 * 1024) {
         gik_set_error("gik_sdp_solve: needs %zu bytes of shared memory per CTA", smem);
@@ -418,11 +461,12 @@ extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double
     int dev = 0, sms = 0, per_sm = 0;
     GIK_CUDA(cudaGetDevice(&dev));
     GIK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GIK_CUDA(cudaFuncSetAttribute(k_sdp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sdp, kThreads, smem));
+    auto kernel = tau ? k_sdp<true> : k_sdp<false>;
+    GIK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     int blocks = sms * per_sm;
     if (blocks > B) blocks = B;
-    k_sdp<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
+    kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
     return gik_check_cuda(cudaGetLastError(), "k_sdp launch");
 }

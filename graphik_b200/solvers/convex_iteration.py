@@ -78,8 +78,9 @@ def make_sdp_opts(params=None):
     return o
 
 
-def sdp_solve_batch(C, W, b, active=None, opts=None):
-    """`gik_sdp_solve` on CUDA tensors C[B,N,N], W[B,M,N], b[B,M] (float64, contiguous); returns a dict of tensors."""
+def sdp_solve_batch(C, W, b, active=None, opts=None, tau=None):
+    """`gik_sdp_solve` on CUDA tensors C[B,N,N], W[B,M,N], b[B,M] (float64, contiguous), tau[M] (0 equality, +1 / -1
+    upper / lower bound; None: all equalities); returns a dict of tensors."""
     import torch
     B, M, N = W.shape
     dev = W.device
@@ -89,11 +90,11 @@ def sdp_solve_batch(C, W, b, active=None, opts=None):
            "resid": torch.full((B,), float("inf"), dtype=torch.float64, device=dev),
            "iters": torch.zeros(B, dtype=torch.int32, device=dev),
            "status": torch.full((B,), 3, dtype=torch.int32, device=dev)}
-    _sdp_launch(C, W, b, active, opts, out)
+    _sdp_launch(C, W, b, active, opts, out, tau)
     return out
 
 
-def _sdp_launch(C, W, b, active, opts, out):
+def _sdp_launch(C, W, b, active, opts, out, tau=None):
     import torch
     B, M, N = W.shape
     for t in (C, W, b):
@@ -103,7 +104,7 @@ def _sdp_launch(C, W, b, active, opts, out):
     o = opts or make_sdp_opts()
     stream = ctypes.c_void_p(torch.cuda.current_stream(W.device).cuda_stream)
     with torch.cuda.device(W.device):
-        _lib.check(_lib.load().gik_sdp_solve(N, M, p(C), p(W), p(b), p(active), B, ctypes.byref(o), p(out["X"]),
+        _lib.check(_lib.load().gik_sdp_solve(N, M, p(C), p(W), p(b), p(tau), p(active), B, ctypes.byref(o), p(out["X"]),
                                              p(out["y"]), p(out["obj"]), p(out["resid"]), p(out["iters"]),
                                              p(out["status"]), stream), "gik_sdp_solve")
 
@@ -139,7 +140,10 @@ class CidgikPlan:
         if graph.dim != 3:
             raise NotImplementedError("graphik_b200 supports dim = 3")
         ids = graph.node_ids
-        self.names = [u for u in ids if u not in ("x", "y")]            # convex_iteration.py:179-180
+        # convex_iteration.py:179-180 removes x and y; obstacles (nodes with a position: anchors, :186-189) are joined to
+        # the other anchors only and to robot nodes by BOUNDED edges only, so they never enter an equality
+        self.obstacle_names = [o["name"] for o in graph.obstacles]
+        self.names = [u for u in ids if u not in ("x", "y") and u not in self.obstacle_names]
         self.anchor_names = ["p0", "q0", "p%d" % n, "q%d" % n]
         self.free = [u for u in self.names if u not in self.anchor_names]  # canonical_point_order (:193)
         sel = [graph.idx(u) for u in self.names]
@@ -230,6 +234,24 @@ class CidgikPlan:
                 WH.append(w)
                 b.append(1.0 if p == q else 2.0)
         WK, WA, WH, b = np.array(WK), np.array(WA), np.array(WH), np.array(b)
+        # -- inequalities (distance_range_constraints, sdp_snl.py:356-398: BOUNDED edges with an obstacle at one end;
+        # anchor_inequality_constraint :586-618).  The reference's own graphs never carry such an edge (SURVEY App. C.1:
+        # obstacle_semantics="reference" -> none); obstacle_semantics="intended" has p_i -- obstacle with LOWER = radius.
+        IK, IA, IH, ib, itau = [], [], [], [], []
+        for oname in self.obstacle_names:
+            o = graph.idx(oname)
+            for j, u in enumerate(self.names):
+                if is_anchor[j]:
+                    continue                                  # both ends anchored: ignored (:364-366)
+                iu = graph.idx(u)
+                for flag, bound, sense in ((graph.below, graph.lower, -1.0), (graph.above, graph.upper, 1.0)):
+                    if flag[iu, o]:
+                        IK.append(coefK[j])
+                        IA.append(coefA[j])
+                        IH.append(-graph.pos[o])
+                        ib.append(bound[iu, o] ** 2)
+                        itau.append(sense)
+        self.n_inequalities = len(ib)
         # an independent subset (the eliminated nodes make many of them repeat each other), chosen on one sample goal
         A0 = self._anchors_numpy(np.asarray(robot.fk_all(q_gen[None]))[0, n][None])[0]
         Wfull = np.hstack([WK, WA.dot(A0) + WH])
@@ -240,7 +262,14 @@ class CidgikPlan:
         keep = np.sort(piv[:int(np.sum(dg > tol * dg[0]))])
         self.keep = keep
         self.WK, self.WA, self.WH, self.b = WK[keep], WA[keep], WH[keep], b[keep]
-        self.M = len(keep)
+        self.tau = np.zeros(len(keep))
+        if self.n_inequalities:
+            self.WK = np.vstack([self.WK, np.array(IK)])
+            self.WA = np.vstack([self.WA, np.array(IA)])
+            self.WH = np.vstack([self.WH, np.array(IH)])
+            self.b = np.concatenate([self.b, np.array(ib)])
+            self.tau = np.concatenate([self.tau, np.array(itau)])
+        self.M = len(self.b)
         # -- V: rows of the free nodes (reference order: graph order), then the homogeneous coordinates
         fsel = [self.names.index(u) for u in self.free]
         self.VK = np.vstack([coefK[fsel], np.zeros((d, nk))])
@@ -265,7 +294,7 @@ class CidgikPlan:
         if key not in self._dev:
             f = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
             g = self.graph
-            self._dev[key] = {k: f(getattr(self, k)) for k in ("WK", "WA", "WH", "b", "VK", "VA", "VH")}
+            self._dev[key] = {k: f(getattr(self, k)) for k in ("WK", "WA", "WH", "b", "VK", "VA", "VH", "tau")}
             self._dev[key]["base"] = f(np.stack([g.pos[g.idx("p0")], g.pos[g.idx("q0")]]))
         return self._dev[key]
 
@@ -285,7 +314,8 @@ class CidgikPlan:
 
 
 def _plan_for(graph):
-    sig = hash((graph.number_of_nodes(), graph.dist.tobytes()))
+    sig = hash((graph.number_of_nodes(), graph.dist.tobytes(), graph.lower.tobytes(), graph.upper.tobytes(),
+                graph.below.tobytes(), graph.above.tobytes()))
     cached = getattr(graph, "_gik_cidgik_cache", None)
     if cached is None or cached[0] != sig:
         cached = (sig, CidgikPlan(graph))
@@ -313,6 +343,7 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
     anchors, W, b, V = plan.assemble(T_goals, device)
     B = W.shape[0]
     dev = W.device
+    tau = plan._tensors(device)["tau"] if plan.n_inequalities else None
     opts = make_sdp_opts(sdp_params)
     f64 = dict(dtype=torch.float64, device=dev)
     C = torch.eye(N, **f64).expand(B, N, N).contiguous() if W_init is None else \
@@ -342,7 +373,7 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
     sdp_iters_max = torch.zeros(max_iters, dtype=torch.int32, device=dev)   # per launch: its slowest program
     n_active = torch.zeros(max_iters, dtype=torch.int32, device=dev)
     for it in range(max_iters):
-        _sdp_launch(Cr, W, b, active, opts, sdp)
+        _sdp_launch(Cr, W, b, active, opts, sdp, tau)
         launches += 1
         on = active.bool()
         code = torch.where((sdp["status"] == 1) & (sdp["resid"] > sdp_accept), torch.full_like(sdp["status"], 3),
@@ -376,7 +407,7 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
         C = eye - torch.matmul(torch.matmul(Qb, torch.eye(Nr, **f64) - Cs), Qb.transpose(1, 2))
     return {"Z": Z, "C": C, "values": values, "eig_sums": eig_sums, "n_iters": n_iters, "feasible": feasible,
             "resid": sdp["resid"], "sdp_iters": sdp_iters, "anchors": anchors, "plan": plan, "launches": launches,
-            "y": sdp["y"], "V": V, "W": W, "b": b, "sdp_iters_max": sdp_iters_max, "n_active": n_active}
+            "y": sdp["y"], "V": V, "W": W, "b": b, "tau": tau, "sdp_iters_max": sdp_iters_max, "n_active": n_active}
 
 
 def solve_batch_with_cidgik(graph, T_goals, as_numpy=False, **kw):
@@ -391,7 +422,7 @@ def solve_batch_with_cidgik(graph, T_goals, as_numpy=False, **kw):
     dev = Z.device
     X = Z[:, -d:, :plan.n_free]                                   # extract_solution (sdp_snl.py:763-780)
     Y = torch.zeros((B, graph.number_of_nodes(), 3), dtype=torch.float64, device=dev)
-    for name in ("p0", "x", "y", "q0"):                           # convex_iteration.py:312-315
+    for name in ["p0", "x", "y", "q0"] + plan.obstacle_names:     # convex_iteration.py:312-315 (+ the other anchors)
         Y[:, graph.idx(name)] = torch.as_tensor(graph.pos[graph.idx(name)], dtype=torch.float64, device=dev)
     Y[:, graph.idx(plan.anchor_names[2])] = anchors[:, 2]         # :308-310
     Y[:, graph.idx(plan.anchor_names[3])] = anchors[:, 3]

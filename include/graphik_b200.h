@@ -283,10 +283,12 @@ int gik_fantope(int32_t n, int32_t d, const double *G, int32_t B, double *C, dou
 /* CIDGIK, the semidefinite programs of the convex iteration: solve_linear_cost_sdp (solvers/sdp_snl.py:874-967,
  * cvxpy -> MOSEK at :952).  MOSEK is closed third-party code outside the reference tree: PARITY UNPINNED; this is a
  * primal-dual interior-point method (HKM direction, Mehrotra predictor-corrector) for B programs of the form
- *     minimise <C, X>  s.t.  w_k^T X w_k = b_k (k < M),  X >= 0 (N x N)
+ *     minimise <C, X>  s.t.  w_k^T X w_k = b_k  (tau_k = 0),  <= b_k  (tau_k = +1),  >= b_k  (tau_k = -1),  X >= 0 (N x N)
  * which is the form every constraint of the reference's program takes (a squared distance between two points, an
  * entry of the identity block) once the host has written the points in the coordinates of the face the feasible set
- * lives on (graphik_b200/solvers/convex_iteration.py).  C[B][N][N], W[B][M][N], b[B][M]; active[B] (may be NULL):
+ * lives on (graphik_b200/solvers/convex_iteration.py); the inequalities are distance_range_constraints' bounds
+ * (sdp_snl.py:356-398, 586-618), each with a slack in a 1 x 1 block of the cone.  C[B][N][N], W[B][M][N], b[B][M];
+ * tau[M] shared by all programs (may be NULL: all equalities); active[B] (may be NULL):
  * programs with active[b] == 0 are skipped and their outputs left untouched.  X[B][N][N], y[B][M] (dual, may be
  * NULL), obj[B] = <C, X>, resid[B] = max(relative primal residual, relative dual residual, relative gap) of the
  * returned iterate, iters[B], status[B].  N <= 32, M <= 96 (GIK_ELIMIT beyond). */
@@ -305,7 +307,7 @@ typedef struct {
 } GikSdpOpts;
 int gik_sdp_default_opts(GikSdpOpts *opts);
 int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const double *b,
-                  const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
+                  const double *tau, const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
                   double *obj, double *resid, int32_t *iters, int32_t *status, void *stream);
 
 #ifdef __cplusplus

@@ -151,3 +151,73 @@ def test_solve_with_cidgik_reference_api():
     assert np.abs(robot.fk_all(q[None])[0, n] - T[0]).max() < 1e-3
     np.testing.assert_allclose(solution["p%d" % n], T[0][:3, 3], atol=1e-12)
     assert solve_with_cidgik(graph, _far_goal()) == (None, None)
+
+
+def _ur10_with_sphere(centre=(0.3, 0.3, 0.2), radius=0.3):
+    """obstacle_semantics="intended": the p_i -- obstacle edges carry LOWER = radius (BELOW), which is what
+    distance_range_constraints (sdp_snl.py:356-398) turns into inequalities; the reference's own graphs never get such
+    an edge."""
+    robot, graph = load_robot("ur10", graph_params={"obstacle_semantics": "intended"})
+    graph.add_spherical_obstacle("o0", np.array(centre), radius)
+    return robot, graph
+
+
+def test_sdp_kernel_with_inequalities_matches_the_numpy_statement():
+    import torch
+    from oracle import cidgik as cg
+    from graphik_b200.solvers.convex_iteration import CidgikPlan, sdp_solve_batch
+    robot, graph = _ur10_with_sphere()
+    plan = CidgikPlan(graph)
+    assert plan.n_inequalities == robot.n - 1 and list(plan.tau[-plan.n_inequalities:]) == [-1.0] * (robot.n - 1)
+    Q, T = random_goals(robot, 16, 13)
+    anchors, W, b, V = plan.assemble(T, device="cuda")
+    C = torch.matmul(V.transpose(1, 2), V).contiguous()
+    tau = torch.as_tensor(plan.tau, dtype=torch.float64, device="cuda")
+    out = sdp_solve_batch(C, W, b, tau=tau)
+    X, y = out["X"].cpu().numpy(), out["y"].cpu().numpy()
+    Cn, Wn, bn = C.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy()
+    seen = set()
+    for k in range(16):
+        A = np.einsum("ki,kj->kij", Wn[k], Wn[k])
+        ref = cg.solve_sdp(Cn[k], A, bn[k], sense=plan.tau)
+        st = int(out["status"][k])
+        seen.add(st)
+        assert st == ref["status"]
+        if st >= 2:
+            continue
+        assert abs(int(out["iters"][k]) - ref["iters"]) <= 1
+        assert abs(float(out["obj"][k]) - ref["obj"]) < 1e-6 * (1 + abs(ref["obj"]))
+        cert = cg.certificate(Cn[k], A, bn[k], X[k], y[k], sense=plan.tau)
+        tol = 1e-6 if st == 0 else 1e-4
+        assert cert["pres"] < tol and cert["gap"] < tol, cert
+        assert cert["min_eig_X"] > -1e-10 and cert["min_eig_S"] > -1e-7 and cert["min_mult"] > -1e-7, cert
+    assert 0 in seen
+
+
+def test_cidgik_keeps_clear_of_an_obstacle():
+    """End result with inequalities on (BASELINE configs[4] 'inequality constraints on', intended obstacle semantics):
+    wherever the iteration ends at rank 3 the joint points stay outside the sphere and the pose is reached; without the
+    obstacle a good part of the same goals run through it."""
+    from graphik_b200.solvers.convex_iteration import solve_batch_with_cidgik
+    centre, radius = np.array([0.3, 0.3, 0.2]), 0.3      # 23 of the 128 generating configurations pass through it
+    robot, graph = _ur10_with_sphere(centre, radius)
+    robot0, graph0 = load_robot("ur10")
+    n = robot.n
+    Q, T = random_goals(robot, 128, 17)
+    out = solve_batch_with_cidgik(graph, T, as_numpy=True)
+    free = solve_batch_with_cidgik(graph0, T, as_numpy=True)
+    pid = [graph.idx("p%d" % i) for i in range(1, n)]
+    clear = np.linalg.norm(out["x"][:, pid] - centre, axis=-1).min(axis=1)
+    clear0 = np.linalg.norm(free["x"][:, [graph0.idx("p%d" % i) for i in range(1, n)]] - centre, axis=-1).min(axis=1)
+    last = np.array([v[~np.isnan(v)][-1] if np.any(~np.isnan(v)) else np.inf for v in out["values"]])
+    done = (out["feasible"] == 0) & (last < 1e-6)
+    assert done.sum() >= 40 and np.sum(clear0 < radius - 1e-2) >= 8, (done.sum(), np.sum(clear0 < radius - 1e-2))
+    assert np.all(clear[done] > radius - 1e-3), np.sort(clear[done])[:5]
+    Tq = robot.fk_all(out["q"])[:, n]
+    assert np.all(np.linalg.norm(Tq[done, :3, 3] - T[done, :3, 3], axis=1) < 1e-2)
+    # goals whose wrist points (fixed by the goal pose) lie inside the sphere have no solution: reported, not returned
+    assert np.sum(out["feasible"] == 1) >= 1
+    # a goal solved without touching the sphere is solved the same way with it (inactive constraints change nothing much)
+    far = (clear0 > radius + 0.2) & (free["feasible"] == 0) & done
+    if far.any():
+        assert np.median(np.abs(out["x"][far][:, :16] - free["x"][far]).max(axis=(1, 2))) < 1e-2
