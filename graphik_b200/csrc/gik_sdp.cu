@@ -17,15 +17,18 @@
 // and the Schur complement of the HKM direction is a Hadamard product,
 //     M_kl = <w_k w_k^T, X w_l w_l^T S^-1> = (w_k^T X w_l) (w_l^T S^-1 w_k).
 //
-// Mapping: one CTA of 128 threads per program, everything in shared memory (N <= 32, M <= 96; a UR10 program has
-// N = 6, M = 15).  Matrix products are spread over the CTA; the factorisations (Cholesky of S, of M and of the trial
-// points of the step-length search -- no eigenvalue problem anywhere) and the triangular solves run on warp 0 with a
-// lane per row.  HBM traffic is the problem data in and the solution out, once.
+// Mapping: one warp per program (32-thread CTAs, 16 per SM), everything in shared memory (N <= 32, M <= 96; a UR10
+// program has N = 6, M = 15, 8 KB).  The factorisations (Cholesky of S, of M and of the trial points of the step-length
+// search -- no eigenvalue problem anywhere) and the triangular solves run with a lane per row, the small matrix
+// products with a lane per entry.  Wider CTAs were measured and dropped: 128 threads 3.7 ms, 64 threads 1.7 ms for the
+// first launch of 1024 UR10 programs (the second warp only waits at barriers), one warp the same latency at twice the
+// programs in flight (16 384 programs per batch: 147 k -> 197 k solves/s).  HBM traffic is the problem data in and the
+// solution out, once.
 #include "gik_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 64;     // a UR10 program has 36-entry matrices: two warps, 8 CTAs per SM at 128 registers
+constexpr int kThreads = 32;     // one warp per program: the matrices have 36-100 entries and half of the work is serial on one warp anyway
 constexpr int kMaxN = 32, kMaxM = 96;
 
 struct SdpArgs {
@@ -54,6 +57,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *scratch)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double s = 0.0;
+#pragma unroll 1
         for (int w = 0; w < kThreads / 32; ++w) s += scratch[w * K + k];
         v[k] = s;
     }
@@ -62,9 +66,11 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *scratch)
 // Out[r x c] = A[r x n] B[n x c], row major
 __device__ __noinline__ void matmul(double *Out, const double *A, const double *Bm, int r, int n, int c)
 {
+#pragma unroll 1
     for (int e = threadIdx.x; e < r * c; e += kThreads) {
         const int i = e / c, j = e % c;
         double s = 0.0;
+#pragma unroll 1
         for (int k = 0; k < n; ++k) s = fma(A[i * n + k], Bm[k * c + j], s);
         Out[e] = s;
     }
@@ -75,6 +81,7 @@ __device__ __noinline__ void matmul(double *Out, const double *A, const double *
 template <int R>
 __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, int lane)
 {
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
         double s[R];
 #pragma unroll
@@ -83,6 +90,7 @@ __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, in
             s[q] = 0.0;
             if (i >= j && i < n) {
                 double t = A[i * n + j];
+#pragma unroll 1
                 for (int k = 0; k < j; ++k) t = fma(-L[i * n + k], L[j * n + k], t);
                 s[q] = t;
             }
@@ -108,16 +116,20 @@ __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, in
 // x <- (L L^T)^-1 x on one warp
 __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
 {
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
         double p = 0.0;
+#pragma unroll 1
         for (int k = lane; k < j; k += 32) p = fma(L[j * n + k], x[k], p);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
         if (lane == 0) x[j] = (x[j] - p) / L[j * n + j];
         __syncwarp();
     }
+#pragma unroll 1
     for (int j = n - 1; j >= 0; --j) {
         double p = 0.0;
+#pragma unroll 1
         for (int k = j + 1 + lane; k < n; k += 32) p = fma(L[k * n + j], x[k], p);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
@@ -133,6 +145,7 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
                                              int bisections)
 {
     auto inside = [&](double alpha) {
+#pragma unroll 1
         for (int e = lane; e < n * n; e += 32) T[e] = fma(alpha, dX[e], X[e]);
         __syncwarp();
         const bool ok = warp_cholesky<1>(T, L, n, lane);
@@ -146,6 +159,7 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
         lo *= 0.7;
         if (lo < 1e-12) return 0.0;
     }
+#pragma unroll 1
     for (int r = 0; r < bisections; ++r) {
         const double mid = 0.5 * (lo + hi);
         if (inside(mid)) lo = mid; else hi = mid;
@@ -155,7 +169,7 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
 
 // LP: the program has inequality rows (slack blocks); the equality-only instantiation carries none of that code
 template <bool LP>
-__global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
+__global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
 {
     extern __shared__ double sm[];
     const int N = a.N, M = a.M, NN = N * N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,16 +179,27 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
     double *bv = G + M * M, *yv = bv + M, *rp = yv + M, *dy = rp + M, *ybest = dy + M, *tau = ybest + M,
            *sv = tau + M, *zv = sv + M, *dsv = zv + M, *dzv = dsv + M, *clp = dzv + M, *red = clp + M;   // red: [2 * 8]
     double *flag = red + 32;                                                           // [4]
+    unsigned char *row_of = reinterpret_cast<unsigned char *>(flag + 4), *col_of = row_of + NN;   // entry -> (i, j)
+#pragma unroll 1
+    for (int e = tid; e < NN; e += kThreads) {
+        row_of[e] = (unsigned char)(e / N);
+        col_of[e] = (unsigned char)(e % N);
+    }
+    __syncthreads();
 
+#pragma unroll 1
     for (int prob = blockIdx.x; prob < a.B; prob += gridDim.x) {
         if (a.active && !a.active[prob]) continue;
         __syncthreads();
+#pragma unroll 1
         for (int e = tid; e < NN; e += kThreads) {
-            const int i = e / N, j = e % N;
+            const int i = row_of[e], j = col_of[e];
             C[e] = a.C[(size_t)prob * NN + e];
             X[e] = S[e] = i == j ? a.o.x0 : 0.0;
         }
+#pragma unroll 1
         for (int e = tid; e < M * N; e += kThreads) W[e] = a.W[(size_t)prob * M * N + e];
+#pragma unroll 1
         for (int k = tid; k < M; k += kThreads) {
             bv[k] = a.b[(size_t)prob * M + k];
             yv[k] = 0.0;
@@ -186,11 +211,14 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
         }
         __syncthreads();
         int n_ineq = 0;
+#pragma unroll 1
         for (int k = 0; LP && k < M; ++k) n_ineq += tau[k] != 0.0;
         double nb, nC;
         {
             double v[2] = {0.0, 0.0};
+#pragma unroll 1
             for (int k = tid; k < M; k += kThreads) v[0] = fma(bv[k], bv[k], v[0]);
+#pragma unroll 1
             for (int e = tid; e < NN; e += kThreads) v[1] = fma(C[e], C[e], v[1]);
             block_sum<2>(v, red);
             nb = 1.0 + sqrt(v[0]);
@@ -199,23 +227,29 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
         int status = GIK_SDP_INACCURATE, it = 0;
         double resid = INFINITY, pobj = 0.0, best_resid = INFINITY, best_obj = 0.0;
         int best_it = 0;
+#pragma unroll 1
         for (it = 0;; ++it) {
             // residuals
             matmul(P, W, X, M, N, N);
+#pragma unroll 1
             for (int e = tid; e < NN; e += kThreads) {
-                const int i = e / N, j = e % N;
+                const int i = row_of[e], j = col_of[e];
                 double s = C[e] - S[e];
+#pragma unroll 1
                 for (int k = 0; k < M; ++k) s = fma(-yv[k] * W[k * N + i], W[k * N + j], s);
                 Rd[e] = s;
             }
             __syncthreads();
+#pragma unroll 1
             for (int k = tid; k < M; k += kThreads) {
                 double s = LP ? bv[k] - tau[k] * sv[k] : bv[k];
+#pragma unroll 1
                 for (int j = 0; j < N; ++j) s = fma(-P[k * N + j], W[k * N + j], s);
                 rp[k] = s;
             }
             __syncthreads();
             double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
             for (int e = tid; e < NN; e += kThreads) {
                 v[0] = fma(X[e], S[e], v[0]);
                 v[1] = fma(C[e], X[e], v[1]);
@@ -223,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 const double t = C[e] - Rd[e];
                 v[3] = fma(t, t, v[3]);
             }
+#pragma unroll 1
             for (int k = tid; k < M; k += kThreads) {
                 v[4] = fma(bv[k], yv[k], v[4]);
                 v[5] = fma(rp[k], rp[k], v[5]);
@@ -247,7 +282,9 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 best_resid = resid;
                 best_obj = pobj;
                 best_it = it;
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) Xbest[e] = X[e];
+#pragma unroll 1
                 for (int k = tid; k < M; k += kThreads) ybest[k] = yv[k];
             } else if (best_resid < 1e-4 && (resid > 10.0 * best_resid || it - best_it >= 3)) {
                 break;
@@ -262,9 +299,12 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 if (lane == 0) flag[0] = ok ? 1.0 : 0.0;
                 if (ok && lane < N) {            // column `lane` of L^-1 into T1
                     const int j = lane;
+#pragma unroll 1
                     for (int i = 0; i < j; ++i) T1[i * N + j] = 0.0;
+#pragma unroll 1
                     for (int i = j; i < N; ++i) {
                         double s = i == j ? 1.0 : 0.0;
+#pragma unroll 1
                         for (int k = j; k < i; ++k) s = fma(-L[i * N + k], T1[k * N + j], s);
                         T1[i * N + j] = s / L[i * N + i];
                     }
@@ -272,9 +312,11 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
             }
             __syncthreads();
             if (flag[0] == 0.0) break;
+#pragma unroll 1
             for (int e = tid; e < NN; e += kThreads) {
-                const int i = e / N, j = e % N;
+                const int i = row_of[e], j = col_of[e];
                 double s = 0.0;
+#pragma unroll 1
                 for (int k = i > j ? i : j; k < N; ++k) s = fma(T1[k * N + i], T1[k * N + j], s);
                 Sinv[e] = s;
             }
@@ -282,10 +324,12 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
             // Schur complement (lower triangle) and its factor
             matmul(Q, W, Sinv, M, N, N);
             __syncthreads();
+#pragma unroll 1
             for (int e = tid; e < M * M; e += kThreads) {
                 const int k = e / M, l = e % M;
                 if (l > k) continue;
                 double u = 0.0, w = 0.0;
+#pragma unroll 1
                 for (int j = 0; j < N; ++j) {
                     u = fma(P[k * N + j], W[l * N + j], u);
                     w = fma(Q[l * N + j], W[k * N + j], w);
@@ -306,23 +350,28 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const bool use_corr = pass == 1;
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) T1[e] = Rd[e] + S[e];
                 __syncthreads();
                 matmul(T2, X, T1, N, N, N);
                 __syncthreads();
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) {
                     double t = T2[e];
-                    if (e / N == e % N) t -= nu;
+                    if (row_of[e] == col_of[e]) t -= nu;
                     if (use_corr) t += corr[e];
                     T2[e] = t;
                 }
                 __syncthreads();
                 matmul(T1, T2, Sinv, N, N, N);
                 __syncthreads();
+#pragma unroll 1
                 for (int k = tid; k < M; k += kThreads) {
                     double s = rp[k];
+#pragma unroll 1
                     for (int i = 0; i < N; ++i) {
                         double r = 0.0;
+#pragma unroll 1
                         for (int j = 0; j < N; ++j) r = fma(T1[i * N + j], W[k * N + j], r);
                         s = fma(W[k * N + i], r, s);
                     }
@@ -335,14 +384,17 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 __syncthreads();
                 if (warp == 0) warp_cholesky_solve(G, dy, M, lane);
                 __syncthreads();
+#pragma unroll 1
                 for (int k = tid; LP && k < M; k += kThreads)
                     if ((LP && tau[k] != 0.0)) {
                         dzv[k] = -tau[k] * yv[k] - zv[k] - tau[k] * dy[k];
                         dsv[k] = ((nu - clp[k]) / zv[k] - sv[k]) - sv[k] / zv[k] * dzv[k];
                     }
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) {
-                    const int i = e / N, j = e % N;
+                    const int i = row_of[e], j = col_of[e];
                     double s = Rd[e];
+#pragma unroll 1
                     for (int k = 0; k < M; ++k) s = fma(-dy[k] * W[k * N + i], W[k * N + j], s);
                     dS[e] = s;
                 }
@@ -350,15 +402,18 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 matmul(T2, X, dS, N, N, N);
                 __syncthreads();
                 if (use_corr) {
+#pragma unroll 1
                     for (int e = tid; e < NN; e += kThreads) T2[e] += corr[e];
                     __syncthreads();
                 }
                 matmul(T1, T2, Sinv, N, N, N);
                 __syncthreads();
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) T2[e] = nu * Sinv[e] - X[e] - T1[e];
                 __syncthreads();
+#pragma unroll 1
                 for (int e = tid; e < NN; e += kThreads) {
-                    const int i = e / N, j = e % N;
+                    const int i = row_of[e], j = col_of[e];
                     dX[e] = 0.5 * (T2[i * N + j] + T2[j * N + i]);
                 }
                 __syncthreads();
@@ -370,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                 __syncthreads();
                 ap = flag[1];
                 ad = flag[2];
+#pragma unroll 1
                 for (int k = 0; LP && k < M; ++k)    // ratio test on the slacks (the same on every thread)
                     if ((LP && tau[k] != 0.0)) {
                         if (dsv[k] < 0.0) ap = fmin(ap, -sv[k] / dsv[k]);
@@ -377,14 +433,17 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
                     }
                 if (pass == 0) {
                     double m[1] = {0.0};
+#pragma unroll 1
                     for (int e = tid; e < NN; e += kThreads)
                         m[0] = fma(fma(ap, dX[e], X[e]), fma(ad, dS[e], S[e]), m[0]);
+#pragma unroll 1
                     for (int k = tid; LP && k < M; k += kThreads)
                         if ((LP && tau[k] != 0.0)) m[0] = fma(fma(ap, dsv[k], sv[k]), fma(ad, dzv[k], zv[k]), m[0]);
                     block_sum<1>(m, red);
                     const double ratio = fmax(m[0] / (N + n_ineq) / mu, 0.0);
                     nu = fmin(1.0, ratio * ratio * ratio) * mu;
                     matmul(corr, dX, dS, N, N, N);
+#pragma unroll 1
                     for (int k = tid; LP && k < M; k += kThreads) clp[k] = dsv[k] * dzv[k];
                     __syncthreads();
                 }
@@ -392,10 +451,12 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
             ap = ap == 1.0 ? 1.0 : a.o.tau * ap;         // a full Newton step when it stays inside the cone
             ad = ad == 1.0 ? 1.0 : a.o.tau * ad;
             __syncthreads();
+#pragma unroll 1
             for (int e = tid; e < NN; e += kThreads) {
                 X[e] = fma(ap, dX[e], X[e]);
                 S[e] = fma(ad, dS[e], S[e]);
             }
+#pragma unroll 1
             for (int k = tid; k < M; k += kThreads) {
                 yv[k] = fma(ad, dy[k], yv[k]);
                 if (LP) {
@@ -408,6 +469,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_sdp(const SdpArgs a)
         }
         __syncthreads();
         const bool use_best = status == GIK_SDP_INACCURATE && best_resid < resid;
+#pragma unroll 1
         for (int e = tid; e < NN; e += kThreads) a.X[(size_t)prob * NN + e] = use_best ? Xbest[e] : X[e];
         if (a.y) for (int k = tid; k < M; k += kThreads) a.y[(size_t)prob * M + k] = use_best ? ybest[k] : yv[k];
         if (tid == 0) {
@@ -452,7 +514,7 @@ extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double
         return GIK_EINVAL;
     }
     a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = iters; a.status = status;
-    const size_t doubles = (size_t)12 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)11 * M + 32 + 4;
+    const size_t doubles = (size_t)12 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)11 * M + 32 + 4 + (2 * (size_t)N * N + 7) / 8;
     const size_t smem = doubles * sizeof(double);
     if (smem > 227 * 1024) {
         gik_set_error("gik_sdp_solve: needs %zu bytes of shared memory per CTA", smem);
