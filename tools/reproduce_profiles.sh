@@ -56,13 +56,13 @@ compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_
 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
 
 # ---- round 2, second part: conjugate-gradient solve and CIDGIK (r2ac .. r2af)
-python -m pytest tests -m gpu -q                                   # gpurun_out/r2ah_pytest.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2ah_bench.json # configs block now ends with BASELINE configs[4]
+python -m pytest tests -m gpu -q                                   # gpurun_out/r2aj_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2aj_bench.json # configs block now ends with BASELINE configs[4]
 python tools/cidgik_bench.py > gpurun_out/r2ae_cidgik.json        # CIDGIK UR10, 1024 goals per batch, CUDA events
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2ae_cidgik_launches.csv \
     python tools/cidgik_bench.py --reps 1 --warmup 1 > /dev/null
 ncu --set full --clock-control none --import-source on -k regex:k_sdp -c 1 -f -o gpurun_out/r2ae_k_sdp \
     python tools/cidgik_bench.py --reps 1 --warmup 0 > /dev/null
 python tools/ncu_summary.py gpurun_out/r2ae_k_sdp.ncu-rep > profiles/r2ae_k_sdp_ur10_b1024.txt
-compute-sanitizer --tool memcheck python tools/sanitize_smoke.py  > gpurun_out/r2ah_memcheck.log
-compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_smoke.py > gpurun_out/r2ah_racecheck.log
+compute-sanitizer --tool memcheck python tools/sanitize_smoke.py  > gpurun_out/r2aj_memcheck.log
+compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_smoke.py > gpurun_out/r2aj_racecheck.log
