@@ -119,6 +119,7 @@ EXPORTS = [
     "gik_init", "gik_bounds_init", "gik_rtr_solve", "gik_joints", "gik_fk", "gik_check_limits",
     "gik_carry_bytes", "gik_carry_init", "gik_rtr_solve_sliced", "gik_workspace_bytes", "gik_fantope",
     "gik_cg_default_opts", "gik_cg_solve", "gik_sdp_default_opts", "gik_sdp_solve",
+    "gik_cidgik_solve",
 ]
 
 _lib = None
@@ -164,6 +165,8 @@ def load():
         "gik_fantope": [i32, i32, vp, i32, vp, vp, vp],
         "gik_sdp_default_opts": [ctypes.POINTER(SdpOpts)],
         "gik_sdp_solve": [i32, i32, vp, vp, vp, vp, vp, i32, ctypes.POINTER(SdpOpts), vp, vp, vp, vp, vp, vp, vp],
+        "gik_cidgik_solve": [i32, i32, i32, vp, vp, vp, vp, vp, i32, ctypes.POINTER(SdpOpts), i32, dbl, dbl, dbl,
+                             vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "gik_cg_default_opts": [ctypes.POINTER(CgOpts)],
         "gik_cg_solve": [vp, vp, vp, i32, ctypes.POINTER(CgOpts), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp],
         "gik_joints": [vp, vp, vp, i32, vp, vp],

@@ -321,10 +321,18 @@ int launch_cg(const GikPlan *p, CgArgs &ca, cudaStream_t st)
         gik_set_error("gik_cg_solve: needs %zu bytes of shared memory per CTA", smem);
         return GIK_ELIMIT;
     }
-    GIK_CUDA(cudaFuncSetAttribute(k_cg<W, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg<W, NPL>, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
+    // shared-memory opt-in and occupancy are properties of (kernel, smem size, device): looked up once
+    static size_t cached_smem = ~(size_t)0;
+    static int cached_per_sm = 0, cached_dev = -1;
+    if (cached_smem != smem || cached_dev != p->device) {
+        GIK_CUDA(cudaFuncSetAttribute(k_cg<W, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int q = 0;
+        GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_cg<W, NPL>, kThreads, smem));
+        cached_per_sm = q < 1 ? 1 : q;
+        cached_smem = smem;
+        cached_dev = p->device;
+    }
+    const int per_sm = cached_per_sm;
     int blocks = p->sm_count * per_sm;
     const int need = (a.B + GPB - 1) / GPB;
     if (blocks > need) blocks = need;

@@ -24,7 +24,7 @@
 // first launch of 1024 UR10 programs (the second warp only waits at barriers), one warp the same latency at twice the
 // programs in flight (16 384 programs per batch: 147 k -> 197 k solves/s).  HBM traffic is the problem data in and the
 // solution out, once.
-#include "gik_common.cuh"
+#include "gik_fantope.cuh"
 
 namespace {
 
@@ -38,6 +38,12 @@ struct SdpArgs {
     GikSdpOpts o;
     double *X, *y, *obj, *resid;
     int32_t *iters, *status;
+    // fused convex iteration (gik_cidgik_solve)
+    const double *Lc;
+    int max_convex, d;
+    double abs_tol, rel_tol, accept;
+    double *Cs, *values, *eig_sums;
+    int32_t *n_convex, *feasible;
 };
 
 // sums of K per-thread values over the CTA, the same on every thread afterwards (fixed order: deterministic)
@@ -167,8 +173,11 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
     return lo;
 }
 
-// LP: the program has inequality rows (slack blocks); the equality-only instantiation carries none of that code
-template <bool LP>
+// LP: the program has inequality rows (slack blocks); the equality-only instantiation carries none of that code.
+// FUSED: the whole convex iteration of a goal (convex_iteration.py:221-266) in the warp that owns it -- program, Fantope
+// step in the coordinates of the face (C <- L (I - sum of the d largest u u^T) L^T with V^T V = L L^T, eigenpairs of
+// L^T X L), stopping test -- instead of one launch per convex iteration and host glue in between.
+template <bool LP, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
 {
     extern __shared__ double sm[];
@@ -179,7 +188,9 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
     double *bv = G + M * M, *yv = bv + M, *rp = yv + M, *dy = rp + M, *ybest = dy + M, *tau = ybest + M,
            *sv = tau + M, *zv = sv + M, *dsv = zv + M, *dzv = dsv + M, *clp = dzv + M, *red = clp + M;   // red: [2 * 8]
     double *flag = red + 32;                                                           // [4]
-    unsigned char *row_of = reinterpret_cast<unsigned char *>(flag + 4), *col_of = row_of + NN;   // entry -> (i, j)
+    double *Lm = flag + 4, *Csm = Lm + NN, *JA = Csm + NN, *JV = JA + N * (N + 1), *lam = JV + N * (N + 1);   // lam: [32]
+    static_assert(!FUSED || kThreads == 32, "the Fantope step runs on the warp that owns the program");
+    unsigned char *row_of = reinterpret_cast<unsigned char *>(lam + 32), *col_of = row_of + NN;   // entry -> (i, j)
 #pragma unroll 1
     for (int e = tid; e < NN; e += kThreads) {
         row_of[e] = (unsigned char)(e / N);
@@ -193,9 +204,8 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
         __syncthreads();
 #pragma unroll 1
         for (int e = tid; e < NN; e += kThreads) {
-            const int i = row_of[e], j = col_of[e];
             C[e] = a.C[(size_t)prob * NN + e];
-            X[e] = S[e] = i == j ? a.o.x0 : 0.0;
+            if (FUSED) Lm[e] = a.Lc[(size_t)prob * NN + e];
         }
 #pragma unroll 1
         for (int e = tid; e < M * N; e += kThreads) W[e] = a.W[(size_t)prob * M * N + e];
@@ -206,13 +216,27 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
             // inequality k: w_k^T X w_k + tau_k s_k = b_k with a slack s_k >= 0 (tau = +1 upper, -1 lower bound) and its
             // dual z_k = -tau_k y_k >= 0 -- a 1 x 1 block of the cone next to X
             tau[k] = LP ? a.tau[k] : 0.0;
-            sv[k] = zv[k] = (LP && tau[k] != 0.0) ? a.o.x0 : 0.0;
-            dsv[k] = dzv[k] = clp[k] = 0.0;
         }
         __syncthreads();
         int n_ineq = 0;
 #pragma unroll 1
         for (int k = 0; LP && k < M; ++k) n_ineq += tau[k] != 0.0;
+        // state of the convex iteration (FUSED; otherwise the loop body runs once)
+        double last_cost = 1e6;
+        int n_convex = 0, feasible = 0, sdp_total = 0;
+        int status = GIK_SDP_INACCURATE, it = 0;
+        double resid = INFINITY, pobj = 0.0;
+#pragma unroll 1
+        for (int cit = 0; cit < (FUSED ? a.max_convex : 1); ++cit) {
+#pragma unroll 1
+        for (int e = tid; e < NN; e += kThreads) X[e] = S[e] = row_of[e] == col_of[e] ? a.o.x0 : 0.0;
+#pragma unroll 1
+        for (int k = tid; k < M; k += kThreads) {
+            yv[k] = 0.0;
+            sv[k] = zv[k] = (LP && tau[k] != 0.0) ? a.o.x0 : 0.0;
+            dsv[k] = dzv[k] = clp[k] = 0.0;
+        }
+        __syncthreads();
         double nb, nC;
         {
             double v[2] = {0.0, 0.0};
@@ -224,8 +248,9 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
             nb = 1.0 + sqrt(v[0]);
             nC = 1.0 + sqrt(v[1]);
         }
-        int status = GIK_SDP_INACCURATE, it = 0;
-        double resid = INFINITY, pobj = 0.0, best_resid = INFINITY, best_obj = 0.0;
+        status = GIK_SDP_INACCURATE;
+        resid = INFINITY;
+        double best_resid = INFINITY, best_obj = 0.0;
         int best_it = 0;
 #pragma unroll 1
         for (it = 0;; ++it) {
@@ -468,15 +493,87 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
             __syncthreads();
         }
         __syncthreads();
-        const bool use_best = status == GIK_SDP_INACCURATE && best_resid < resid;
+        if (status == GIK_SDP_INACCURATE && best_resid < resid) {        // the best iterate is the answer
 #pragma unroll 1
-        for (int e = tid; e < NN; e += kThreads) a.X[(size_t)prob * NN + e] = use_best ? Xbest[e] : X[e];
-        if (a.y) for (int k = tid; k < M; k += kThreads) a.y[(size_t)prob * M + k] = use_best ? ybest[k] : yv[k];
+            for (int e = tid; e < NN; e += kThreads) X[e] = Xbest[e];
+#pragma unroll 1
+            for (int k = tid; k < M; k += kThreads) yv[k] = ybest[k];
+            pobj = best_obj;
+            resid = best_resid;
+            __syncthreads();
+        }
+        if (!FUSED) break;
+        // ---- convex_iteration.py:236-266 for this goal
+        sdp_total += it;
+        const int code = status == GIK_SDP_INACCURATE && resid > a.accept ? GIK_SDP_NUMERIC : status;
+        if (code >= GIK_SDP_INFEASIBLE) { feasible = code - 1; break; }      // INFEASIBLE / SOLVER_ERROR (:237-245)
+        if (tid == 0) a.values[(size_t)prob * a.max_convex + cit] = pobj;
+        // Zs = L^T X L (symmetrised as eigh reads it) into the Jacobi buffer, V = I
+        matmul(T1, X, Lm, N, N, N);
+        __syncthreads();
+        const int ld = N + 1;
+#pragma unroll 1
+        for (int e = tid; e < NN; e += kThreads) {
+            const int i = row_of[e], j = col_of[e];
+            double zij = 0.0, zji = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                zij = fma(Lm[k * N + i], T1[k * N + j], zij);
+                zji = fma(Lm[k * N + j], T1[k * N + i], zji);
+            }
+            JA[i * ld + j] = 0.5 * (zij + zji);
+            JV[i * ld + j] = i == j ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        int rank;
+        double mine;
+        const unsigned top = gik_warp_fantope_eig(JA, JV, lam, N, a.d, lane, &rank, &mine);
+        double small[1] = {lane < N && rank < N - a.d ? mine : 0.0};       // sum of the N - d smallest eigenvalues
+        block_sum<1>(small, red);
+        if (tid == 0) a.eig_sums[(size_t)prob * a.max_convex + cit] = small[0];
+        // Cs = I - sum over the d largest of u u^T (into T2), C <- L Cs L^T
+#pragma unroll 1
+        for (int e = tid; e < NN; e += kThreads) {
+            const int i = row_of[e], j = col_of[e];
+            double acc = i == j ? 1.0 : 0.0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k)
+                if (top >> k & 1u) acc = fma(-JV[i * ld + k], JV[j * ld + k], acc);
+            Csm[e] = acc;
+        }
+        __syncthreads();
+        matmul(T1, Lm, Csm, N, N, N);
+        __syncthreads();
+#pragma unroll 1
+        for (int e = tid; e < NN; e += kThreads) {
+            const int i = row_of[e], j = col_of[e];
+            double acc = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) acc = fma(T1[i * N + k], Lm[j * N + k], acc);
+            C[e] = acc;
+        }
+        __syncthreads();
+        ++n_convex;
+        const double change = last_cost - pobj;                              // :262-266
+        if (fabs(change) <= a.abs_tol || pobj <= a.abs_tol || fabs(change) / fabs(last_cost) < a.rel_tol) break;
+        last_cost = pobj;
+        }   // convex iterations
+        __syncthreads();
+#pragma unroll 1
+        for (int e = tid; e < NN; e += kThreads) {
+            a.X[(size_t)prob * NN + e] = X[e];
+            if (FUSED) a.Cs[(size_t)prob * NN + e] = n_convex ? Csm[e] : (row_of[e] == col_of[e] ? 1.0 : 0.0);
+        }
+        if (a.y) for (int k = tid; k < M; k += kThreads) a.y[(size_t)prob * M + k] = yv[k];
         if (tid == 0) {
-            a.obj[prob] = use_best ? best_obj : pobj;
-            a.resid[prob] = use_best ? best_resid : resid;
-            a.iters[prob] = it;
+            a.obj[prob] = pobj;
+            a.resid[prob] = resid;
+            a.iters[prob] = FUSED ? sdp_total : it;
             a.status[prob] = status;
+            if (FUSED) {
+                a.n_convex[prob] = n_convex;
+                a.feasible[prob] = feasible;
+            }
         }
     }
 }
@@ -493,42 +590,84 @@ extern "C" int gik_sdp_default_opts(GikSdpOpts *o)
     return GIK_OK;
 }
 
+static int launch_sdp(SdpArgs &a, bool fused, void *stream)
+{
+    const int N = a.N, M = a.M;
+    if (N > kMaxN || M > kMaxM) {
+        gik_set_error("gik_sdp_solve: N = %d, M = %d exceed the limits %d, %d", N, M, kMaxN, kMaxM);
+        return GIK_ELIMIT;
+    }
+    if (!(a.o.tol > 0.0) || a.o.maxiter < 1 || !(a.o.tau > 0.0 && a.o.tau < 1.0) || !(a.o.x0 > 0.0)) {
+        gik_set_error("gik_sdp_solve: tol > 0, maxiter >= 1, 0 < tau < 1, x0 > 0 required");
+        return GIK_EINVAL;
+    }
+    const size_t doubles = (size_t)14 * N * N + (size_t)2 * N * (N + 1) + (size_t)3 * M * N + (size_t)M * M +
+                           (size_t)11 * M + 32 + 4 + 32 + (2 * (size_t)N * N + 7) / 8;
+    const size_t smem = doubles * sizeof(double);
+    if (smem > 227 * 1024) {
+        gik_set_error("gik_sdp_solve: needs %zu bytes of shared memory per CTA", smem);
+        return GIK_ELIMIT;
+    }
+    // shared-memory opt-in, occupancy and SM count are properties of (kernel, smem size, device): looked up once
+    static size_t cached_smem[4] = {~(size_t)0, ~(size_t)0, ~(size_t)0, ~(size_t)0};
+    static int cached_blocks[4] = {0, 0, 0, 0}, cached_dev[4] = {-1, -1, -1, -1};
+    const int v = (a.tau ? 1 : 0) + (fused ? 2 : 0);
+    void (*kernel)(SdpArgs) = v == 0 ? k_sdp<false, false> : v == 1 ? k_sdp<true, false>
+                            : v == 2 ? k_sdp<false, true> : k_sdp<true, true>;
+    int dev = 0;
+    GIK_CUDA(cudaGetDevice(&dev));
+    if (cached_smem[v] != smem || cached_dev[v] != dev) {
+        int sms = 0, per_sm = 0;
+        GIK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GIK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+        cached_blocks[v] = sms * (per_sm < 1 ? 1 : per_sm);
+        cached_smem[v] = smem;
+        cached_dev[v] = dev;
+    }
+    int blocks = cached_blocks[v];
+    if (blocks > a.B) blocks = a.B;
+    kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
+    return gik_check_cuda(cudaGetLastError(), "k_sdp launch");
+}
+
 extern "C" int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const double *b,
-                             const double *tau, const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
-                             double *obj, double *resid, int32_t *iters, int32_t *status, void *stream)
+                             const double *tau, const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X,
+                             double *y, double *obj, double *resid, int32_t *iters, int32_t *status, void *stream)
 {
     if (B == 0) return GIK_OK;
     if (B < 0 || N < 1 || M < 1 || !C || !W || !b || !X || !obj || !resid || !iters || !status) {
         gik_set_error("gik_sdp_solve: bad argument");
         return GIK_EINVAL;
     }
-    if (N > kMaxN || M > kMaxM) {
-        gik_set_error("gik_sdp_solve: N = %d, M = %d exceed the limits %d, %d", N, M, kMaxN, kMaxM);
-        return GIK_ELIMIT;
-    }
     SdpArgs a;
+    memset(&a, 0, sizeof(a));
     a.N = N; a.M = M; a.B = B; a.C = C; a.W = W; a.b = b; a.tau = tau; a.active = active;
     if (opts) a.o = *opts; else gik_sdp_default_opts(&a.o);
-    if (!(a.o.tol > 0.0) || a.o.maxiter < 1 || !(a.o.tau > 0.0 && a.o.tau < 1.0) || !(a.o.x0 > 0.0)) {
-        gik_set_error("gik_sdp_solve: tol > 0, maxiter >= 1, 0 < tau < 1, x0 > 0 required");
+    a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = iters; a.status = status;
+    return launch_sdp(a, false, stream);
+}
+
+extern "C" int gik_cidgik_solve(int32_t N, int32_t M, int32_t d, const double *G, const double *Lc, const double *W,
+                                const double *b, const double *tau, int32_t B, const GikSdpOpts *opts,
+                                int32_t max_iters, double abs_eig_sum_tol, double rel_eig_sum_tol, double sdp_accept,
+                                double *X, double *y, double *Cs, double *values, double *eig_sums, int32_t *n_iters,
+                                int32_t *feasible, double *obj, double *resid, int32_t *sdp_iters, int32_t *status,
+                                void *stream)
+{
+    if (B == 0) return GIK_OK;
+    if (B < 0 || N < 1 || M < 1 || d < 0 || d > N || max_iters < 1 || !G || !Lc || !W || !b || !X || !Cs || !values ||
+        !eig_sums || !n_iters || !feasible || !obj || !resid || !sdp_iters || !status) {
+        gik_set_error("gik_cidgik_solve: bad argument");
         return GIK_EINVAL;
     }
-    a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = iters; a.status = status;
-    const size_t doubles = (size_t)12 * N * N + (size_t)3 * M * N + (size_t)M * M + (size_t)11 * M + 32 + 4 + (2 * (size_t)N * N + 7) / 8;
-    const size_t smem = doubles * sizeof(double);
-    if (smem > 227 * 1024) {
-        gik_set_error("gik_sdp_solve: needs %zu bytes of shared memory per CTA", smem);
-        return GIK_ELIMIT;
-    }
-    int dev = 0, sms = 0, per_sm = 0;
-    GIK_CUDA(cudaGetDevice(&dev));
-    GIK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    auto kernel = tau ? k_sdp<true> : k_sdp<false>;
-    GIK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GIK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    int blocks = sms * per_sm;
-    if (blocks > B) blocks = B;
-    kernel<<<blocks, kThreads, smem, (cudaStream_t)stream>>>(a);
-    return gik_check_cuda(cudaGetLastError(), "k_sdp launch");
+    SdpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.M = M; a.B = B; a.C = G; a.W = W; a.b = b; a.tau = tau;
+    if (opts) a.o = *opts; else gik_sdp_default_opts(&a.o);
+    a.X = X; a.y = y; a.obj = obj; a.resid = resid; a.iters = sdp_iters; a.status = status;
+    a.Lc = Lc; a.max_convex = max_iters; a.d = d;
+    a.abs_tol = abs_eig_sum_tol; a.rel_tol = rel_eig_sum_tol; a.accept = sdp_accept;
+    a.Cs = Cs; a.values = values; a.eig_sums = eig_sums; a.n_convex = n_iters; a.feasible = feasible;
+    return launch_sdp(a, true, stream);
 }

@@ -327,14 +327,17 @@ def _plan_for(graph):
 # the convex iteration, batched
 # ------------------------------------------------------------------------------------------------------------------
 def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel_eig_sum_tol=1e-3, W_init=None,
-                         sdp_params=None, sdp_accept=1e-3, device="cuda"):
+                         sdp_params=None, sdp_accept=1e-3, device="cuda", fused=True):
     """convex_iterate_sdp_snl_graph (convex_iteration.py:160-276; ranges=True, sparse=False, closed_form=True) for
     every goal of T_goals[B,4,4] at once.  Returns a dict of CUDA tensors: Z[B,N,N] (the last SDP solution of each
     goal), C, values[B,max_iters] (SDP optimum per convex iteration, NaN beyond the last), eig_sums (sum of the N - d
     smallest eigenvalues of Z, the reference's eig_value_sum_vs_iterations), n_iters[B], feasible[B] (0 feasible,
     1 infeasible, 2 solver error), resid[B], sdp_iters[B] (interior-point iterations, summed), anchors, plan.
     A program the solver leaves with a residual above `sdp_accept` counts as a solver error (the reference's
-    SOLVER_ERROR branch, :241-244); below it an inaccurate answer is used as cvxpy's 'optimal_inaccurate' is."""
+    SOLVER_ERROR branch, :241-244); below it an inaccurate answer is used as cvxpy's 'optimal_inaccurate' is.
+    fused=True (default, C = I start only): the whole loop of a goal runs inside one kernel launch (`gik_cidgik_solve`);
+    fused=False: one `gik_sdp_solve` + one `gik_fantope` launch per convex iteration with the bookkeeping in torch --
+    the same arithmetic up to the rounding of the small matrix products."""
     import torch
     if not torch.cuda.is_available():
         raise _lib.GikError("graphik_b200 needs a CUDA device (B200); there is no CPU fallback")
@@ -372,7 +375,19 @@ def convex_iterate_batch(graph, T_goals, max_iters=10, abs_eig_sum_tol=1e-6, rel
     launches = 0
     sdp_iters_max = torch.zeros(max_iters, dtype=torch.int32, device=dev)   # per launch: its slowest program
     n_active = torch.zeros(max_iters, dtype=torch.int32, device=dev)
-    for it in range(max_iters):
+    fused = fused and W_init is None
+    if fused:
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        Lcc, Cs = Lc.contiguous(), torch.empty((B, Nr, Nr), **f64)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().gik_cidgik_solve(
+                Nr, plan.M, d, p(Cr), p(Lcc), p(W), p(b), p(tau), B, ctypes.byref(opts), int(max_iters),
+                float(abs_eig_sum_tol), float(rel_eig_sum_tol), float(sdp_accept), p(sdp["X"]), p(sdp["y"]), p(Cs),
+                p(values), p(eig_sums), p(n_iters), p(feasible), p(sdp["obj"]), p(sdp["resid"]), p(sdp_iters),
+                p(sdp["status"]), stream), "gik_cidgik_solve")
+        launches, it = 1, 1
+    for it in range(0 if fused else max_iters):
         _sdp_launch(Cr, W, b, active, opts, sdp, tau)
         launches += 1
         on = active.bool()

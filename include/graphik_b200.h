@@ -310,6 +310,23 @@ int gik_sdp_solve(int32_t N, int32_t M, const double *C, const double *W, const 
                   const double *tau, const int32_t *active, int32_t B, const GikSdpOpts *opts, double *X, double *y,
                   double *obj, double *resid, int32_t *iters, int32_t *status, void *stream);
 
+/* CIDGIK, the whole convex iteration of B goals in one launch: convex_iterate_sdp_snl_graph (solvers/
+ * convex_iteration.py:160-276; dense, closed-form Fantope step) with the programs in the form gik_sdp_solve takes.
+ * Per goal, in the warp that owns it: C = I, solve, Fantope step, stopping test on the change of the optimum
+ * (:262-266), at most max_iters times.  The Fantope step is taken in the coordinates of the face: with Z = V X V^T and
+ * V^T V = L L^T the non-zero eigenpairs of Z are those of L^T X L, so the caller passes G[B][N][N] = V^T V (= the cost
+ * matrix of the first program, C = I) and Lc[B][N][N] = L (lower), and the cost of the next program is
+ * L (I - sum over the d largest of u u^T) L^T.  W, b, tau, opts, X, y, obj, resid, status: as gik_sdp_solve (values of
+ * the last program solved for each goal); Cs[B][N][N]: the last I - sum u u^T; values / eig_sums[B][max_iters]: optimum
+ * and sum of the smallest eigenvalues per convex iteration (the caller pre-fills them, e.g. with NaN); n_iters[B];
+ * feasible[B]: 0, 1 (INFEASIBLE, :237-240) or 2 (SOLVER_ERROR, :241-244: non-finite, or stopped with resid > sdp_accept);
+ * sdp_iters[B]: interior-point iterations, summed. */
+int gik_cidgik_solve(int32_t N, int32_t M, int32_t d, const double *G, const double *Lc, const double *W,
+                     const double *b, const double *tau, int32_t B, const GikSdpOpts *opts, int32_t max_iters,
+                     double abs_eig_sum_tol, double rel_eig_sum_tol, double sdp_accept, double *X, double *y,
+                     double *Cs, double *values, double *eig_sums, int32_t *n_iters, int32_t *feasible, double *obj,
+                     double *resid, int32_t *sdp_iters, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

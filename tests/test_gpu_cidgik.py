@@ -86,15 +86,17 @@ def test_sdp_kernel_edge_cases():
                         torch.zeros((1, 10), dtype=torch.float64, device="cuda"))
 
 
-def test_convex_iteration_matches_the_numpy_statement():
-    """The batched loop against oracle.convex_iterate run in the same coordinates: same number of convex iterations,
-    same SDP optima, same end points (to the accuracy a chain of up to 10 interior-point solves leaves)."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_convex_iteration_matches_the_numpy_statement(fused):
+    """The batched loop (one fused launch / one launch per convex iteration) against oracle.convex_iterate run in the
+    same coordinates: same number of convex iterations, same SDP optima, same end points (to the accuracy a chain of up
+    to 10 interior-point solves leaves)."""
     from oracle import cidgik as cg
     from graphik_b200.solvers.convex_iteration import convex_iterate_batch
     robot, graph = load_robot("ur10")
     n = robot.n
     Q, T = random_goals(robot, 4, 0)
-    out = convex_iterate_batch(graph, T)
+    out = convex_iterate_batch(graph, T, fused=fused)
     plan = out["plan"]
     Wn, bn, Vn, an = (out[k].cpu().numpy() for k in ("W", "b", "V", "anchors"))
     vals, nit, Z = out["values"].cpu().numpy(), out["n_iters"].cpu().numpy(), out["Z"].cpu().numpy()
@@ -221,3 +223,29 @@ def test_cidgik_keeps_clear_of_an_obstacle():
     far = (clear0 > radius + 0.2) & (free["feasible"] == 0) & done
     if far.any():
         assert np.median(np.abs(out["x"][far][:, :16] - free["x"][far]).max(axis=(1, 2))) < 1e-2
+
+
+@pytest.mark.parametrize("with_sphere", [False, True])
+def test_fused_convex_iteration_equals_the_launch_per_iteration_one(with_sphere):
+    """gik_cidgik_solve (the whole loop of a goal inside one launch) against gik_sdp_solve + gik_fantope + torch
+    bookkeeping: the same arithmetic up to the rounding of the small matrix products."""
+    from graphik_b200.solvers.convex_iteration import convex_iterate_batch
+    robot, graph = _ur10_with_sphere() if with_sphere else load_robot("ur10")
+    Q, T = random_goals(robot, 256, 29)
+    a = convex_iterate_batch(graph, T, fused=True)
+    b = convex_iterate_batch(graph, T, fused=False)
+    assert a["launches"] == 1 and b["launches"] >= 6
+    fa, fb = a["feasible"].cpu().numpy(), b["feasible"].cpu().numpy()
+    na, nb = a["n_iters"].cpu().numpy(), b["n_iters"].cpu().numpy()
+    va, vb = a["values"].cpu().numpy(), b["values"].cpu().numpy()
+    assert np.mean(fa == fb) >= 0.99 and (with_sphere or np.all(fa == 0))
+    ok = (fa == 0) & (fb == 0)
+    np.testing.assert_allclose(va[ok, 0], vb[ok, 0], rtol=1e-8)                       # the C = I programs
+    np.testing.assert_allclose(a["eig_sums"].cpu().numpy()[ok, 0], b["eig_sums"].cpu().numpy()[ok, 0], rtol=1e-6, atol=1e-9)
+    assert np.mean(na[ok] == nb[ok]) >= 0.9
+    same = ok & (na == nb)
+    dz = np.abs(a["Z"].cpu().numpy()[same] - b["Z"].cpu().numpy()[same]).max(axis=(1, 2))
+    assert np.median(dz) < 1e-5 and np.mean(dz < 1e-2) >= 0.9
+    np.testing.assert_allclose(np.sum(a["sdp_iters"].cpu().numpy()[same]), np.sum(b["sdp_iters"].cpu().numpy()[same]), rtol=0.05)
+    dc = np.abs(a["C"].cpu().numpy()[same] - b["C"].cpu().numpy()[same]).max(axis=(1, 2))
+    assert np.median(dc) < 1e-4

@@ -82,17 +82,20 @@ def main():
     for name in ("ur10", "kuka"):
         robot, graph = load_workload(name)
         _, T = goals_for(robot, 3, seed=2)
-        out = convex_iterate_batch(graph, T, max_iters=2, sdp_params={"maxiter": 4}, sdp_accept=float("inf"))
-        torch.cuda.synchronize()
-        assert int(out["n_iters"].max()) == 2
-        done.append("%s/cidgik" % name)
+        for fused in (True, False):          # gik_cidgik_solve / gik_sdp_solve + gik_fantope per convex iteration
+            out = convex_iterate_batch(graph, T, max_iters=2, sdp_params={"maxiter": 4}, sdp_accept=float("inf"),
+                                       fused=fused)
+            torch.cuda.synchronize()
+            assert int(out["n_iters"].max()) == 2
+        done.append("%s/cidgik fused + per-iteration" % name)
     from helpers import load_robot as _lr
     robot, graph = _lr("ur10", graph_params={"obstacle_semantics": "intended"})
     graph.add_spherical_obstacle("o0", np.array([0.3, 0.3, 0.2]), 0.3)
     _, T = goals_for(robot, 3, seed=2)
-    convex_iterate_batch(graph, T, max_iters=2, sdp_params={"maxiter": 4}, sdp_accept=float("inf"))
-    torch.cuda.synchronize()
-    done.append("ur10+sphere/cidgik with inequalities")
+    for fused in (True, False):
+        convex_iterate_batch(graph, T, max_iters=2, sdp_params={"maxiter": 4}, sdp_accept=float("inf"), fused=fused)
+        torch.cuda.synchronize()
+    done.append("ur10+sphere/cidgik with inequalities fused + per-iteration")
     print("sanitize smoke ok:", " ".join(done))
 
 
