@@ -83,7 +83,8 @@ __device__ __noinline__ void matmul(double *Out, const double *A, const double *
 }
 
 // Lower Cholesky factor of the n x n matrix A (leading dimension n) into L (may alias A) on ONE warp, lane r owning
-// the rows r, r + 32, ... (R of them: n <= 32 R).  False (on every lane) when a pivot is not positive and finite.
+// the rows r, r + 32, ... (R of them: n <= 32 R); the diagonal of L is stored INVERTED.  False (on every lane) when a
+// pivot is not positive and finite.
 template <int R>
 __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, int lane)
 {
@@ -106,20 +107,20 @@ __device__ __noinline__ bool warp_cholesky(const double *A, double *L, int n, in
         for (int q = 1; q < R; ++q) mine = (j >> 5) == q ? s[q] : mine;
         const double dj = __shfl_sync(GIK_FULL_MASK, mine, j & 31, 32);
         if (!(dj > 0.0) || !isfinite(dj)) return false;
-        const double r = sqrt(dj);
+        const double rinv = rsqrt(dj);           // one reciprocal square root instead of a square root and a division
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int i = lane + 32 * q;
-            if (i == j) L[i * n + j] = r;
-            else if (i > j && i < n) L[i * n + j] = s[q] / r;
+            if (i == j) L[i * n + j] = rinv;     // the diagonal holds 1 / L_jj: every later use divides by it
+            else if (i > j && i < n) L[i * n + j] = s[q] * rinv;
         }
         __syncwarp();
     }
     return true;
 }
 
-// x <- (L L^T)^-1 x on one warp
+// x <- (L L^T)^-1 x on one warp (L as warp_cholesky leaves it: inverted diagonal)
 __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int n, int lane)
 {
 #pragma unroll 1
@@ -129,7 +130,7 @@ __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int
         for (int k = lane; k < j; k += 32) p = fma(L[j * n + k], x[k], p);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
-        if (lane == 0) x[j] = (x[j] - p) / L[j * n + j];
+        if (lane == 0) x[j] = (x[j] - p) * L[j * n + j];
         __syncwarp();
     }
 #pragma unroll 1
@@ -139,7 +140,7 @@ __device__ __noinline__ void warp_cholesky_solve(const double *L, double *x, int
         for (int k = j + 1 + lane; k < n; k += 32) p = fma(L[k * n + j], x[k], p);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(GIK_FULL_MASK, p, o, 32);
-        if (lane == 0) x[j] = (x[j] - p) / L[j * n + j];
+        if (lane == 0) x[j] = (x[j] - p) * L[j * n + j];
         __syncwarp();
     }
 }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
                         double s = i == j ? 1.0 : 0.0;
 #pragma unroll 1
                         for (int k = j; k < i; ++k) s = fma(-L[i * N + k], T1[k * N + j], s);
-                        T1[i * N + j] = s / L[i * N + i];
+                        T1[i * N + j] = s * L[i * N + i];
                     }
                 }
             }
