@@ -174,6 +174,66 @@ __device__ __noinline__ double warp_max_step(const double *X, const double *dX, 
     return lo;
 }
 
+// The two step-length searches of an iteration side by side (n <= 16): lanes 0-15 search X + alpha dX, lanes 16-31
+// S + alpha dS, each half with its own candidate, both running the same instruction stream (a half that has finished,
+// or whose trial factorisation has already failed, is predicated off).  Same candidates and same arithmetic per trial
+// as warp_max_step.  T, L: two n x n scratch matrices each.  Returns this lane's half's step (lanes 0-15: primal).
+__device__ __noinline__ double warp_dual_max_step(const double *X, const double *dX, const double *S, const double *dS,
+                                                  double *Ta, double *Tb, double *La, double *Lb, int n, int lane,
+                                                  int bisections)
+{
+    const int half = lane >> 4, hl = lane & 15;
+    const double *Mx = half ? S : X, *Dx = half ? dS : dX;
+    double *T = half ? Tb : Ta, *L = half ? Lb : La;
+    int phase = 0, count = 0;            // 0: full step, 1: backtracking, 2: bisection, 3: done
+    double hi = 1.0, lo = 0.7, result = 0.0;
+#pragma unroll 1
+    while (__any_sync(GIK_FULL_MASK, phase != 3)) {
+        const bool busy = phase != 3;
+        const double alpha = phase == 0 ? 1.0 : (phase == 1 ? lo : 0.5 * (lo + hi));
+        if (busy) {
+#pragma unroll 1
+            for (int e = hl; e < n * n; e += 16) T[e] = fma(alpha, Dx[e], Mx[e]);
+        }
+        __syncwarp();
+        // Cholesky of T on this half (row hl), inverted diagonal as warp_cholesky; ok: no pivot failed so far
+        bool ok = busy;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            double t = 0.0;
+            if (ok && hl >= j && hl < n) {
+                t = T[hl * n + j];
+#pragma unroll 1
+                for (int k = 0; k < j; ++k) t = fma(-L[hl * n + k], L[j * n + k], t);
+            }
+            const double dj = __shfl_sync(GIK_FULL_MASK, t, j, 16);
+            ok = ok && dj > 0.0 && isfinite(dj);
+            if (!__any_sync(GIK_FULL_MASK, ok)) break;
+            const double rinv = ok ? rsqrt(dj) : 0.0;
+            __syncwarp();
+            if (ok && hl >= j && hl < n) L[hl * n + j] = hl == j ? rinv : t * rinv;
+            __syncwarp();
+        }
+        __syncwarp();
+        if (phase == 0) {
+            if (ok) { result = 1.0; phase = 3; } else phase = 1;
+        } else if (phase == 1) {
+            if (ok) {
+                phase = bisections > 0 ? 2 : 3;
+                result = lo;
+            } else {
+                hi = lo;
+                lo *= 0.7;
+                if (lo < 1e-12) { result = 0.0; phase = 3; }
+            }
+        } else if (phase == 2) {
+            if (ok) lo = 0.5 * (lo + hi); else hi = 0.5 * (lo + hi);
+            if (++count == bisections) { result = lo; phase = 3; }
+        }
+    }
+    return result;
+}
+
 // LP: the program has inequality rows (slack blocks); the equality-only instantiation carries none of that code.
 // FUSED: the whole convex iteration of a goal (convex_iteration.py:221-266) in the warp that owns it -- program, Fantope
 // step in the coordinates of the face (C <- L (I - sum of the d largest u u^T) L^T with V^T V = L L^T, eigenpairs of
@@ -444,9 +504,15 @@ __global__ void __launch_bounds__(kThreads, 16) k_sdp(const SdpArgs a)
                 }
                 __syncthreads();
                 if (warp == 0) {                       // step lengths to the boundary of the cone
-                    const double sp = warp_max_step(X, dX, T1, L, N, lane, pass ? 4 : 0);
-                    const double sd = warp_max_step(S, dS, T1, L, N, lane, pass ? 4 : 0);
-                    if (lane == 0) { flag[1] = sp; flag[2] = sd; }
+                    if (N <= 16) {                     // both searches at once, one per half warp (T2, corr are free here)
+                        const double st = warp_dual_max_step(X, dX, S, dS, T1, T2, L, corr, N, lane, pass ? 4 : 0);
+                        if (lane == 0) flag[1] = st;
+                        if (lane == 16) flag[2] = st;
+                    } else {
+                        const double sp = warp_max_step(X, dX, T1, L, N, lane, pass ? 4 : 0);
+                        const double sd = warp_max_step(S, dS, T1, L, N, lane, pass ? 4 : 0);
+                        if (lane == 0) { flag[1] = sp; flag[2] = sd; }
+                    }
                 }
                 __syncthreads();
                 ap = flag[1];
