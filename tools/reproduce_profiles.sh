@@ -56,18 +56,18 @@ compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_
 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
 
 # ---- round 2, second part: conjugate-gradient solve and CIDGIK (r2ac .. r2aj)
-python -m pytest tests -m gpu -q                                   # gpurun_out/r2ak_pytest.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2ak_bench.json # configs block now ends with BASELINE configs[4]
-for b in 1024 4096 16384 65536; do python tools/cidgik_bench.py --batch $b --reps 5 --warmup 2; done > gpurun_out/r2ak_cidgik_batches.jsonl
-python tools/cidgik_bench.py --robot kuka --batch 1024 --reps 5 --warmup 2 >> gpurun_out/r2ak_cidgik_batches.jsonl
-python tools/cidgik_bench.py --robot lwa4d --batch 1024 --reps 5 --warmup 2 >> gpurun_out/r2ak_cidgik_batches.jsonl
-ncu --set full --clock-control none --import-source on -k regex:k_sdp -c 1 -f -o gpurun_out/r2ak_k_sdp \
+python -m pytest tests -m gpu -q                                   # gpurun_out/r2al_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2al_bench.json # configs block now ends with BASELINE configs[4]
+for b in 1024 4096 16384 65536; do python tools/cidgik_bench.py --batch $b --reps 5 --warmup 2; done > gpurun_out/r2al_cidgik_batches.jsonl
+python tools/cidgik_bench.py --robot kuka --batch 1024 --reps 5 --warmup 2 >> gpurun_out/r2al_cidgik_batches.jsonl
+python tools/cidgik_bench.py --robot lwa4d --batch 1024 --reps 5 --warmup 2 >> gpurun_out/r2al_cidgik_batches.jsonl
+ncu --set full --clock-control none --import-source on -k regex:k_sdp -c 1 -f -o gpurun_out/r2al_k_sdp \
     python tools/cidgik_bench.py --batch 16384 --reps 1 --warmup 0 > /dev/null
-python tools/ncu_summary.py gpurun_out/r2ak_k_sdp.ncu-rep > profiles/r2ak_k_cidgik_fused_ur10_b16384.txt
+python tools/ncu_summary.py gpurun_out/r2al_k_sdp.ncu-rep > profiles/r2al_k_cidgik_fused_ur10_b16384.txt
 # (earlier kernel versions: r2ae = 64-thread CTAs, r2ag = + one-slot Cholesky; same tool with --batch 1024, and
 #  ncu --metrics gpu__time_duration.sum ... --csv --log-file gpurun_out/r2ae_cidgik_launches.csv for the launch list)
-compute-sanitizer --tool memcheck python tools/sanitize_smoke.py  > gpurun_out/r2ak_memcheck.log
-compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_smoke.py > gpurun_out/r2ak_racecheck.log
+compute-sanitizer --tool memcheck python tools/sanitize_smoke.py  > gpurun_out/r2al_memcheck.log
+compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitize_smoke.py > gpurun_out/r2al_racecheck.log
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2ak_cidgik_launches.csv \
     python tools/cidgik_bench.py --reps 1 --warmup 1 > /dev/null
 # (r2aj_*: the same commands at the commit before the fused launch, i.e. one k_sdp + one k_fantope launch per convex iteration)
