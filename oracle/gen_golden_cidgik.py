@@ -75,6 +75,38 @@ def main():
             out[key + "A"] = np.array(A)
             out[key + "b"] = np.array(b)
             out[key + "n_inequalities"] = np.array(sum(len(v) for v in ineq.values()))
+    # The inequality form.  The reference's own graphs never carry a robot -- obstacle edge, so
+    # distance_range_constraints returns nothing for them; the function that WOULD build the row,
+    # anchor_inequality_constraint (sdp_snl.py:586-618), is called here directly for every free joint point of the
+    # UR10 against one sphere (lower bound = radius), on a graph that holds the sphere as the reference adds it.
+    robot, graph = ru.load_ur10()
+    n = robot.n
+    centre, radius = np.array([0.3, 0.3, 0.2]), 0.3
+    graph.add_spherical_obstacle("o0", centre, radius)
+    np.random.seed(1)
+    T = robot.pose(robot.random_configuration(), "p%d" % n)
+    anchors = {"p0": graph.nodes["p0"][POS], "q0": graph.nodes["q0"][POS], "p%d" % n: T.trans,
+               "q%d" % n: T.trans + T.rot.as_matrix()[:, 2], "o0": graph.nodes["o0"][POS]}   # :186-189: POS -> anchor
+    G = nx.DiGraph(graph)
+    G.remove_node("x")
+    G.remove_node("y")
+    ccd = sdp_snl.distance_constraints_graph(G, anchors, False, ee_cost=False, angle_limits=True)
+    (clique, (A, b, mapping, augmented)), = ccd.items()
+    assert len(sdp_snl.distance_range_constraints(G, ccd, anchors)) == 0       # as shipped: nothing
+    names = sorted((k for k in mapping if isinstance(k, str)), key=lambda k: mapping[k])
+    rows, rhs, nodes = [], [], []
+    for i in range(1, n):
+        _, (Ai, bi) = sdp_snl.anchor_inequality_constraint(ccd, frozenset(("p%d" % i, "o0")), radius, anchors, False)
+        rows.append(Ai)
+        rhs.append(bi)
+        nodes.append("p%d" % i)
+    out["ineq_T_goal"] = T.as_matrix()
+    out["ineq_order"] = np.array(names)
+    out["ineq_nodes"] = np.array(nodes)
+    out["ineq_A"] = np.array(rows)                 # <A, Z> <= b
+    out["ineq_b"] = np.array(rhs)
+    out["ineq_centre"], out["ineq_radius"] = centre, np.array(radius)
+    out["ineq_n_equalities"] = np.array(len(A))    # the sphere adds no equality (anchor -- anchor pairs are skipped)
     path = os.path.join(ROOT, "tests", "golden", "cidgik_constraints.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items() if k.endswith("_A")})

@@ -128,3 +128,41 @@ def test_infeasible_program_is_reported():
     out = cg.convex_iterate(graph.node_ids, graph.dist, _anchors(graph, T),
                             np.asarray(graph.realization_points(np.random.RandomState(7).uniform(-2, 2, robot.n))))
     assert not out["feasible"] and out["status"] == cg.STATUS_INFEASIBLE
+
+
+def test_inequality_rows_match_the_reference_form():
+    """The plan's inequality rows (obstacle_semantics="intended") against anchor_inequality_constraint
+    (sdp_snl.py:586-618), called by the golden script for every free joint point of the UR10 and one sphere: both
+    expressions take the same value on matrices of the feasible face (lifted true configurations and a mixture of two
+    of them, which has rank 6), with the same sense.  As shipped, the reference's distance_range_constraints returns
+    nothing even with the sphere in its graph (the golden script asserts it)."""
+    from graphik_b200.solvers.convex_iteration import CidgikPlan
+    gold = golden("cidgik_constraints")
+    robot, graph = load_robot("ur10", graph_params={"obstacle_semantics": "intended"})
+    centre, radius = gold["ineq_centre"], float(gold["ineq_radius"])
+    graph.add_spherical_obstacle("o0", centre, radius)
+    plan = CidgikPlan(graph)
+    n = robot.n
+    assert plan.n_inequalities == n - 1 and plan.M == int(np.sum(plan.tau == 0)) + n - 1
+    assert int(gold["ineq_n_equalities"]) == plan.n_distance_constraints        # the sphere adds no equality
+    T = gold["ineq_T_goal"]
+    anchors, W, b, V = [t.numpy()[0] for t in plan.assemble(T[None], device="cpu")]
+    order = [str(u) for u in gold["ineq_order"]]
+    perm = [order.index(u) for u in plan.free] + [len(order), len(order) + 1, len(order) + 2]
+    rows = W[plan.tau != 0]
+    rhs = b[plan.tau != 0]
+    assert np.all(plan.tau[plan.tau != 0] == -1.0)                              # lower bounds: w^T Zr w >= r^2
+    # two configurations with the same end-effector pose do not come for free: use matrices of the face built from the
+    # product's own coordinates instead -- Zr = R R^T with the hom block forced to I
+    rng = np.random.RandomState(3)
+    for trial in range(3):
+        R = rng.randn(plan.Nr, 3 + trial)                                      # rank 3, 4, 5
+        R[-3:, :3], R[-3:, 3:] = np.eye(3), 0.0
+        Zr = R.dot(R.T)
+        Z = V.dot(Zr).dot(V.T)
+        assert np.abs(Z[-3:, -3:] - np.eye(3)).max() < 1e-12
+        for k, u in enumerate(str(v) for v in gold["ineq_nodes"]):
+            A_ref = gold["ineq_A"][k][np.ix_(perm, perm)]
+            ref = np.sum(A_ref * Z) - gold["ineq_b"][k]                         # reference: <A, Z> - b <= 0
+            mine = -(rows[k].dot(Zr).dot(rows[k]) - rhs[k])                     # product: -(w^T Zr w - r^2) <= 0
+            assert abs(ref - mine) < 1e-10 * (1 + abs(ref)), (u, ref, mine)
