@@ -1,4 +1,6 @@
-// gik_sdp.cu -- the semidefinite programs of CIDGIK's convex iteration, batched.
+// gik_sdp.cu -- the semidefinite programs of CIDGIK's convex iteration, batched:
+// gik_sdp_solve (one program per goal per launch) and gik_cidgik_solve (the whole convex iteration of a goal in one
+// launch: programs, Fantope steps and the stopping test of solvers/convex_iteration.py:221-266).
 //
 // Reference: solve_linear_cost_sdp (solvers/sdp_snl.py:874-967) hands
 //     minimise <C, Z>  s.t.  <A_k, Z> = b_k,  Z[-d:, -d:] = I,  Z >= 0
@@ -16,14 +18,18 @@
 //     minimise <C, X>  s.t.  w_k^T X w_k = b_k (k < M),  X >= 0          (dual: S = C - sum y_k w_k w_k^T >= 0)
 // and the Schur complement of the HKM direction is a Hadamard product,
 //     M_kl = <w_k w_k^T, X w_l w_l^T S^-1> = (w_k^T X w_l) (w_l^T S^-1 w_k).
+// Inequality rows (distance_range_constraints, sdp_snl.py:356-398: lower / upper bounds on the distance to an
+// obstacle) carry a slack in a 1 x 1 block of the cone: w_k^T X w_k + tau_k s_k = b_k, s_k >= 0.
 //
-// Mapping: one warp per program (32-thread CTAs, 16 per SM), everything in shared memory (N <= 32, M <= 96; a UR10
+// Mapping: one warp per program (32-thread CTAs, 20 per SM), everything in shared memory (N <= 32, M <= 96; a UR10
 // program has N = 6, M = 15, 8 KB).  The factorisations (Cholesky of S, of M and of the trial points of the step-length
 // search -- no eigenvalue problem anywhere) and the triangular solves run with a lane per row, the small matrix
 // products with a lane per entry.  Wider CTAs were measured and dropped: 128 threads 3.7 ms, 64 threads 1.7 ms for the
 // first launch of 1024 UR10 programs (the second warp only waits at barriers), one warp the same latency at twice the
-// programs in flight (16 384 programs per batch: 147 k -> 197 k solves/s).  HBM traffic is the problem data in and the
-// solution out, once.
+// programs in flight (16 384 programs per batch: 147 k -> 197 k solves/s).  The code is kept small on purpose (loops
+// not unrolled, helpers not inlined, one body for predictor and corrector): with 20 warps per SM at different places of
+// the kernel, instruction fetch was the largest stall of the 7 k-instruction version.  HBM traffic is the problem data
+// in and the solution out, once.
 #include "gik_fantope.cuh"
 
 namespace {
