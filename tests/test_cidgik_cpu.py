@@ -166,3 +166,18 @@ def test_inequality_rows_match_the_reference_form():
             ref = np.sum(A_ref * Z) - gold["ineq_b"][k]                         # reference: <A, Z> - b <= 0
             mine = -(rows[k].dot(Zr).dot(rows[k]) - rhs[k])                     # product: -(w^T Zr w - r^2) <= 0
             assert abs(ref - mine) < 1e-10 * (1 + abs(ref)), (u, ref, mine)
+
+
+def test_obstacles_with_reference_semantics_change_nothing():
+    """The reference's obstacles are anchors joined to the other anchors only: the program of KUKA +
+    table_environment() is the program of the bare KUKA; with the intended semantics every free joint point gets one
+    lower bound per sphere (600 rows -- beyond the kernel's 96, reported by gik_sdp_solve as GIK_ELIMIT)."""
+    from helpers import load_kuka_table
+    from graphik_b200.solvers.convex_iteration import CidgikPlan
+    bare = CidgikPlan(load_robot("kuka")[1])
+    table = CidgikPlan(load_kuka_table()[1])
+    assert (table.N, table.Nr, table.M, table.n_inequalities) == (bare.N, bare.Nr, bare.M, 0)
+    for k in ("WK", "WA", "WH", "b", "VK", "VA", "VH"):
+        np.testing.assert_array_equal(getattr(table, k), getattr(bare, k))
+    intended = CidgikPlan(load_kuka_table(graph_params={"obstacle_semantics": "intended"})[1])
+    assert intended.n_inequalities == 100 * 6 and intended.M == bare.M + 600
